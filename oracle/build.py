@@ -1,0 +1,98 @@
+"""oracle/build.py -- TEST INFRASTRUCTURE ONLY.
+
+Builds the two CPU checkers:
+
+* ``oracle/_build/libref_rules.so``  -- our plain-C restatement (ref_rules.c);
+* ``oracle/_ref/src/cython/bitboard*.so`` -- the REFERENCE'S OWN Cython bitboard,
+  compiled from the source where it lies under /root/reference (never copied
+  into this repo; only the compiled module lands in the git-ignored
+  ``oracle/_ref/``).  Skipped when /root/reference is absent (GPU box): the
+  prebuilt file travels with the snapshot.
+
+Only tests/, __graft_entry__ (build + smoke) and bench.py's cpu_baseline /
+``--impl reference`` legs may import this module.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+import sysconfig
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD_DIR = os.path.join(HERE, "_build")
+REF_OUT = os.path.join(HERE, "_ref")
+REFERENCE_ROOT = os.environ.get("OTHELLO_REFERENCE_ROOT", "/root/reference")
+
+ORACLE_LIB = os.path.join(BUILD_DIR, "libref_rules.so")
+
+
+def _newer(target: str, *sources: str) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def build_oracle(force: bool = False) -> str:
+    """gcc -O3 -fopenmp the C restatement; returns the path of the .so."""
+    src = os.path.join(HERE, "ref_rules.c")
+    hdr = os.path.join(HERE, "ref_rules.h")
+    if not force and _newer(ORACLE_LIB, src, hdr):
+        return ORACLE_LIB
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    cmd = ["gcc", "-O3", "-march=x86-64-v2", "-fopenmp", "-shared", "-fPIC", "-std=c11",
+           "-Wall", "-Wextra", "-o", ORACLE_LIB, src, "-lm"]
+    subprocess.run(cmd, check=True)
+    return ORACLE_LIB
+
+
+def ref_bitboard_path() -> str | None:
+    d = os.path.join(REF_OUT, "src", "cython")
+    if not os.path.isdir(d):
+        return None
+    for f in sorted(os.listdir(d)):
+        if f.startswith("bitboard") and f.endswith(".so"):
+            return os.path.join(d, f)
+    return None
+
+
+def build_ref(force: bool = False) -> str | None:
+    """Compile the reference's Cython bitboard into oracle/_ref (outputs only).
+
+    The .pyx/.pxd are read in place; the generated C goes to a temp dir and is
+    discarded; only the extension module is kept.  Flags follow the reference's
+    setup.py:11-30 (-O3, boundscheck/wraparound off, cdivision on).
+    """
+    have = ref_bitboard_path()
+    pyx = os.path.join(REFERENCE_ROOT, "src", "cython", "bitboard.pyx")
+    if not os.path.exists(pyx):
+        return have                      # GPU box: use what travelled
+    if have and not force and os.path.getmtime(have) >= os.path.getmtime(pyx):
+        return have
+    import numpy as np
+    out_dir = os.path.join(REF_OUT, "src", "cython")
+    os.makedirs(out_dir, exist_ok=True)
+    ext = sysconfig.get_config_var("EXT_SUFFIX")
+    target = os.path.join(out_dir, "bitboard" + ext)
+    with tempfile.TemporaryDirectory(prefix="refbuild_") as tmp:
+        c_file = os.path.join(tmp, "bitboard.c")
+        subprocess.run([sys.executable, "-m", "cython", "-3",
+                        "-X", "boundscheck=False", "-X", "wraparound=False", "-X", "cdivision=True",
+                        pyx, "-o", c_file], check=True)
+        inc = sysconfig.get_paths()["include"]
+        subprocess.run(["gcc", "-O3", "-shared", "-fPIC", "-fwrapv", "-w",
+                        "-DNPY_NO_DEPRECATED_API=NPY_1_7_API_VERSION",
+                        "-I", inc, "-I", np.get_include(), c_file, "-o", target], check=True)
+    return target
+
+
+def main() -> None:
+    print("oracle:", build_oracle(force="--force" in sys.argv))
+    print("oracle/_ref:", build_ref(force="--force" in sys.argv))
+
+
+if __name__ == "__main__":
+    main()

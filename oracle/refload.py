@@ -1,0 +1,82 @@
+"""oracle/refload.py -- TEST INFRASTRUCTURE ONLY.
+
+Loads the REFERENCE ITSELF for pinning the oracle:
+
+* ``ref_bitboard_class()`` -- the reference's compiled Cython ``OthelloBitboard``
+  from ``oracle/_ref`` (built by ``oracle/build.py``; travels to the GPU box as a
+  prebuilt .so), imported under its own module name ``src.cython.bitboard``.
+* ``reference_python()`` -- the reference's pure-Python modules (MCTS, network,
+  batched self-play) imported straight from /root/reference.  Only available in
+  the build container; used by ``oracle/gen_golden.py`` to write the fixtures in
+  ``tests/golden/``.  Nothing that runs on the GPU box calls it.
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.util
+import os
+import sys
+import types
+
+from . import build as _build
+
+
+def ref_bitboard_class():
+    """The reference's own OthelloBitboard (Cython), or None if not built."""
+    path = _build.build_ref()
+    if path is None:
+        return None
+    name = "src.cython.bitboard"
+    if name in sys.modules and getattr(sys.modules[name], "__file__", None) == path:
+        return sys.modules[name].OthelloBitboard
+    # The extension was cythonized as src.cython.bitboard; give it that package context.
+    for pkg in ("src", "src.cython"):
+        if pkg not in sys.modules:
+            m = types.ModuleType(pkg)
+            m.__path__ = []          # namespace-like
+            sys.modules[pkg] = m
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    sys.modules["src.cython"].bitboard = mod
+    return mod.OthelloBitboard
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(_build.REFERENCE_ROOT, "src", "mcts"))
+
+
+def reference_python():
+    """Import the reference's Python hot-path modules from /root/reference.
+
+    Returns a namespace with MCTS, MCTSNode, BatchMCTS, ParallelSelfPlayWorker,
+    SelfPlayWorker, OthelloResNet, OthelloBitboard.  Build-container only.
+    """
+    if not reference_available():
+        raise RuntimeError("reference sources not present (this only works in the build container)")
+    Board = ref_bitboard_class()
+    if Board is None:
+        raise RuntimeError("oracle/_ref is not built")
+    root = _build.REFERENCE_ROOT
+    # make the real 'src' package resolvable while keeping the compiled bitboard we just loaded
+    bb = sys.modules["src.cython.bitboard"]
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        if k != "src.cython.bitboard":
+            del sys.modules[k]
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import src  # noqa: F401  (the reference's package)
+    import src.cython as _c
+    sys.modules["src.cython.bitboard"] = bb
+    _c.bitboard = bb
+    ns = types.SimpleNamespace()
+    ns.OthelloBitboard = bb.OthelloBitboard
+    ns.MCTSNode = importlib.import_module("src.mcts.node").MCTSNode
+    ns.MCTS = importlib.import_module("src.mcts.mcts").MCTS
+    psp = importlib.import_module("src.train.parallel_self_play")
+    ns.BatchMCTS = psp.BatchMCTS
+    ns.ParallelSelfPlayWorker = psp.ParallelSelfPlayWorker
+    ns.SelfPlayWorker = importlib.import_module("src.train.self_play").SelfPlayWorker
+    ns.OthelloResNet = importlib.import_module("src.model.net").OthelloResNet
+    return ns
