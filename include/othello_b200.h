@@ -1,0 +1,192 @@
+/*
+ * othello_b200.h -- C ABI of libothello_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the reference's self-play hot path.  The reference has no
+ * FFI of its own: the boundary is Python duck typing at four call sites
+ * (SURVEY.md section 8(b)).  Each entry point below names the reference interface
+ * it stands behind (paths relative to the reference repository); the Python
+ * classes in othello_reinforcement_learning_test_b200/ bind these with ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every function returns an int status (0 = OTH_OK, <0 =
+ *     error, text via oth_last_error()); nothing throws across the boundary;
+ *   - opaque handles own device memory and are released by *_destroy;
+ *   - batched arrays are caller-allocated structure-of-arrays; `mem` says where
+ *     they live: OTH_MEM_DEVICE (device pointers, asynchronous on the context
+ *     stream) or OTH_MEM_HOST (host pointers; the call copies in/out and returns
+ *     when the results are in the caller's buffers);
+ *   - one context is used by one host thread at a time (the reference is
+ *     single-threaded under the GIL); every context owns one CUDA stream;
+ *   - bit i of a board word is square i = row*8+col, A1 = bit 0
+ *     (src/cython/bitboard.pxd:18-22); `self` is always the side to move.
+ *   - there is no CPU fallback: without a CUDA device oth_ctx_create fails.
+ */
+#ifndef OTHELLO_B200_H
+#define OTHELLO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OTH_OK 0
+#define OTH_ERR_CUDA (-1)
+#define OTH_ERR_ARG (-2)
+#define OTH_ERR_STATE (-3)
+#define OTH_ERR_CAPACITY (-4)
+#define OTH_ERR_UNSUPPORTED (-5)
+
+#define OTH_MEM_DEVICE 0
+#define OTH_MEM_HOST 1
+
+#define OTH_ACTIONS 65 /* 64 squares + pass (64) */
+
+typedef struct oth_ctx oth_ctx;
+typedef struct oth_net oth_net;
+typedef struct oth_search oth_search;
+typedef struct oth_selfplay oth_selfplay;
+
+/* ---- library / context -------------------------------------------------- */
+const char* oth_last_error(void);
+const char* oth_version(void);
+int oth_device_count(int* count);
+int oth_ctx_create(int device, oth_ctx** out);
+int oth_ctx_destroy(oth_ctx* ctx);
+int oth_ctx_sync(oth_ctx* ctx);
+/* cudaStream_t of the context, as an integer, for callers that enqueue their own work */
+uint64_t oth_ctx_stream(oth_ctx* ctx);
+/* kernels launched through this context so far (bench.py: gpu_launches) */
+uint64_t oth_ctx_launch_count(oth_ctx* ctx);
+/* Per-category kernel timing with CUDA events on the context stream (off by default).
+ * Categories: 0 = network forward, 1 = tree kernels, 2 = self-play move kernels.
+ * oth_ctx_timing_read synchronises, returns the summed milliseconds / launch counts since the last
+ * read (arrays of 3) and resets the accumulators. */
+int oth_ctx_timing_enable(oth_ctx* ctx, int on);
+int oth_ctx_timing_read(oth_ctx* ctx, double* ms_out, uint64_t* count_out);
+
+/* ---- bitboard: src/cython/bitboard.pyx --------------------------------------- */
+/* OthelloBitboard.get_legal_moves_bits / _compute_legal_moves (bitboard.pyx:135-158,187-193) */
+int oth_legal_moves(oth_ctx* ctx, const uint64_t* self_b, const uint64_t* opp_b, uint64_t* legal_out,
+                    int64_t n, int mem);
+/* _get_flip_bits (bitboard.pyx:116-133); pos[i] in 0..63, anything else yields 0 */
+int oth_flips(oth_ctx* ctx, const uint64_t* self_b, const uint64_t* opp_b, const int32_t* pos,
+              uint64_t* flips_out, int64_t n, int mem);
+/* OthelloBitboard.make_move (bitboard.pyx:195-247) in place, every reject path included;
+ * ok_out[i] = 1 if applied, 0 if rejected (state untouched).  move_count may be NULL. */
+int oth_make_move(oth_ctx* ctx, uint64_t* self_b, uint64_t* opp_b, int32_t* move_count,
+                  const int32_t* action, uint8_t* ok_out, int64_t n, int mem);
+/* is_terminal + get_winner + get_stone_counts (bitboard.pyx:249-298).  Any output may be NULL. */
+int oth_terminal_winner(oth_ctx* ctx, const uint64_t* self_b, const uint64_t* opp_b,
+                        uint8_t* terminal_out, int8_t* winner_out, int32_t* counts_out /* n*2 */,
+                        int64_t n, int mem);
+/* get_tensor_input (bitboard.pyx:300-323): float32 [n,3,8,8] = self, opp, legal planes */
+int oth_tensor_input(oth_ctx* ctx, const uint64_t* self_b, const uint64_t* opp_b, float* out,
+                     int64_t n, int mem);
+/* perft under REF rules (pass = one ply, terminal = leaf); golden values in SURVEY.md 8(c) */
+int oth_perft(oth_ctx* ctx, uint64_t self_b, uint64_t opp_b, int depth, uint64_t* nodes_out);
+/* benchmark.py:18-40 play_random_game x n_games, one game per thread, from the start position.
+ * total_plies_out / winner_hist_out[3] (get_winner == -1,0,+1) are HOST scalars; the per-game
+ * arrays (final boards, plies) are optional and live where `mem` says. */
+int oth_random_playouts(oth_ctx* ctx, int64_t n_games, uint64_t seed, int64_t* total_plies_out,
+                        int64_t* winner_hist_out, uint64_t* final_self, uint64_t* final_opp,
+                        int32_t* plies, int mem);
+
+/* ---- network: src/model/net.py OthelloResNet ------------------------------------ */
+#define OTH_NET_ENGINE_TCGEN05 0 /* bf16 tcgen05/TMEM implicit-GEMM trunk (product path) */
+#define OTH_NET_ENGINE_SIMT 1    /* CUDA-core validation kernel, same rounding points */
+
+#define OTH_NET_OUT_LOGPROBS 0   /* log_softmax, what model(x) returns (net.py:94) */
+#define OTH_NET_OUT_PROBS 1      /* exp(log_softmax) as mcts.py:191 */
+#define OTH_NET_OUT_PRIORS 2     /* masked to legal moves and renormalised as node.py:71-80 */
+
+int oth_net_create(oth_ctx* ctx, int num_blocks, int num_filters, oth_net** out);
+int oth_net_destroy(oth_net* net);
+/* number of float32 values oth_net_load_weights expects */
+int64_t oth_net_param_count(const oth_net* net);
+/* `flat` = the reference state_dict's floating-point tensors concatenated in key order
+ * (SURVEY.md 8(a) R-NN; num_batches_tracked skipped), HOST float32.  BatchNorm (eval mode,
+ * eps 1e-5) is folded into bf16 conv weights + fp32 bias inside. */
+int oth_net_load_weights(oth_net* net, const float* flat, int64_t count);
+int oth_net_set_engine(oth_net* net, int engine);
+/* OthelloResNet.forward on n positions given as bitboards (the (3,8,8) planes are built
+ * in-kernel).  policy_out float32 [n,65] in `out_kind`; value_out float32 [n]. */
+int oth_net_forward(oth_net* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n,
+                    float* policy_out, float* value_out, int out_kind, int mem);
+
+/* ---- tree search: src/mcts/mcts.py, src/mcts/node.py, BatchMCTS ------------------ */
+#define OTH_FLAG_ROOT_N_SUM 1u   /* root N = completed sims (canonical); default: stays 0 (mcts.py:152-172) */
+#define OTH_FLAG_Q_CANONICAL 2u  /* negate child Q in select; default: un-negated (node.py:113,119) */
+#define OTH_FLAG_WINNER_BLACK 4u /* self-play labels from black's view; default: parallel_self_play.py:397-404 */
+#define OTH_FLAG_EVAL_HASHNET 8u /* built-in integer test evaluator instead of the network */
+
+int oth_search_create(oth_ctx* ctx, int64_t max_games, int max_simulations, oth_search** out);
+int oth_search_destroy(oth_search* s);
+/* MCTS(model, device, c_puct, dirichlet_alpha, dirichlet_epsilon) (mcts.py:27-47) */
+int oth_search_configure(oth_search* s, double c_puct, double dirichlet_alpha, double dirichlet_epsilon,
+                         uint32_t flags);
+/* fresh roots (mcts.py:71: no tree reuse) for n <= max_games positions */
+int oth_search_begin(oth_search* s, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, int mem);
+/* External-evaluator mode (parity with identical network outputs):
+ *   collect: one selection per game (the very first call after begin returns the roots);
+ *            need_eval[i] = 0 where the leaf was terminal and has been backed up already.
+ *   apply:   expand the collected leaves with probs[n,65] / value[n] and back up. */
+int oth_search_collect(oth_search* s, uint64_t* leaf_self, uint64_t* leaf_opp, uint8_t* need_eval, int mem);
+int oth_search_apply(oth_search* s, const float* probs, const float* value, int mem);
+/* MCTS.search / BatchMCTS.search_batch (mcts.py:49-98, parallel_self_play.py:80-170) fully on the
+ * device with `net` (or the hash-net when OTH_FLAG_EVAL_HASHNET).  Call after oth_search_begin. */
+int oth_search_run(oth_search* s, oth_net* net, int num_simulations, int add_dirichlet_noise, uint64_t seed);
+/* root child statistics: visits int32 [n,65], q float64 [n,65] (0 for non-children),
+ * n_evals int32 [n].  Any may be NULL. */
+int oth_search_results(oth_search* s, int32_t* visits, double* q, int32_t* n_evals, int mem);
+/* get_policy_distribution (node.py:147-182): float32 [n,65] for temperature 0 or 1 (others: powf) */
+int oth_search_policy(oth_search* s, double temperature, float* policy_out, int mem);
+
+/* ---- self-play: src/train/parallel_self_play.py ---------------------------------- */
+typedef struct {
+    int32_t num_simulations;        /* mcts.num_simulations */
+    int32_t temperature_threshold;  /* self_play.temperature_threshold */
+    int32_t add_dirichlet_noise;
+    int32_t concurrent_games;       /* device-resident game slots (num_parallel_games) */
+    double c_puct, dirichlet_alpha, dirichlet_epsilon;
+    uint32_t flags;                 /* OTH_FLAG_* */
+    uint32_t reserved;
+    uint64_t seed;
+} oth_selfplay_config;
+
+/* one training sample, packed (expanded to (f32[3,8,8], f32[65], float) by the Python shim) */
+typedef struct {
+    uint64_t self_b, opp_b, legal;  /* get_tensor_input planes */
+    int32_t game;                   /* episode index within the run */
+    int16_t ply;
+    int8_t value;                   /* winner * player (parallel_self_play.py:404) */
+    uint8_t n_children;
+    uint16_t visits[OTH_ACTIONS];   /* root child visit counts; policy = visits / sum */
+    uint16_t pad[3];                /* sizeof(oth_sample) == 168 */
+} oth_sample;
+
+int oth_selfplay_create(oth_ctx* ctx, const oth_selfplay_config* cfg, oth_selfplay** out);
+int oth_selfplay_destroy(oth_selfplay* sp);
+/* ParallelSelfPlayWorker.execute_episodes(num_episodes) (parallel_self_play.py:282-322): plays
+ * num_episodes games to completion with `net` (NULL + OTH_FLAG_EVAL_HASHNET = test evaluator).
+ * n_samples_out / n_evals_out are HOST scalars. */
+int oth_selfplay_run(oth_selfplay* sp, oth_net* net, int64_t num_episodes, int64_t* n_samples_out,
+                     int64_t* n_evals_out);
+/* copy the samples of the last run into a caller buffer (HOST or DEVICE) */
+int oth_selfplay_fetch(oth_selfplay* sp, oth_sample* out, int64_t capacity, int mem);
+/* device pointer + count of the last run's samples (for NCCL all-gather without a host hop) */
+int oth_selfplay_samples_device(oth_selfplay* sp, const oth_sample** dev_ptr_out, int64_t* count_out);
+
+/* ---- diagnostics ---------------------------------------------------------------------- */
+/* One accumulation chain of tcgen05.mma (M=128, N=n, K=16*k_steps, bf16 -> fp32) over a caller
+ * supplied shared-memory image; descriptor fields (byte offsets into the image, LBO/SBO in bytes,
+ * per-k-step advance) are the caller's.  d_out: HOST float32 [128][n].  Used by the tests to pin
+ * the no-swizzle K-major descriptor semantics the convolution kernel relies on. */
+int oth_debug_umma_probe(oth_ctx* ctx, const void* smem_image, int image_bytes, int n, int k_steps,
+                         uint32_t a_off, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep,
+                         uint32_t b_off, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep, float* d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTHELLO_B200_H */

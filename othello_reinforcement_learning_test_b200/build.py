@@ -1,0 +1,83 @@
+"""In-tree build of libothello_b200.so with nvcc for sm_100a (no torch involved).
+
+    python -m othello_reinforcement_learning_test_b200.build [--force] [--verbose]
+
+The shared object lands next to this file so that it travels with the repository
+snapshot to the GPU box (it is git-ignored, not gpurun-ignored).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
+LIB_PATH = os.path.join(PKG_DIR, "libothello_b200.so")
+OBJ_DIR = os.path.join(PKG_DIR, "build")
+
+SOURCES = ["context.cu", "board_ops.cu", "net.cu", "net_tc.cu", "umma_probe.cu", "search.cu", "selfplay.cu"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
+    "--expt-relaxed-constexpr",
+    "-I", INCLUDE,
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (need CUDA 12.9 for sm_100a)")
+
+
+def _deps(src: str):
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs.append(os.path.join(INCLUDE, "othello_b200.h"))
+    return [src] + hdrs
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    nvcc = _nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    sources = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    objs = []
+    procs = []
+    for s in sources:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(OBJ_DIR, s.replace(".cu", ".o"))
+        objs.append(obj)
+        if not force and os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in _deps(src)):
+            continue
+        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd))
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            print(f"--- nvcc failed on {s} ---\n{out}", file=sys.stderr)
+        elif verbose and out.strip():
+            print(out)
+    if failed:
+        raise RuntimeError("nvcc compilation failed")
+    need_link = force or procs or not os.path.exists(LIB_PATH) or any(
+        os.path.getmtime(o) > os.path.getmtime(LIB_PATH) for o in objs)
+    if need_link:
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", LIB_PATH, *objs, "-lcuda"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

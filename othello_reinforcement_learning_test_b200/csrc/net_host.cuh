@@ -1,0 +1,38 @@
+// net_host.cuh -- host-side network object shared by net.cu, net_tc.cu, search.cu, selfplay.cu
+#pragma once
+#include "common.cuh"
+#include "net_common.cuh"
+
+namespace oth {
+
+struct NetHost {
+    oth_ctx* ctx = nullptr;
+    int blocks = 0, F = 0;
+    int engine = 0;
+    bool loaded = false;
+    void* d_w_tc = nullptr;
+    float* d_w_simt = nullptr;
+    float* d_small = nullptr;
+    NetDev dev{};
+    uint64_t evals = 0;     // positions evaluated so far (bench bookkeeping)
+
+    size_t w_tc_elems() const { return (size_t)9 * 16 * F + (size_t)2 * blocks * 9 * F * F; }
+    size_t w_simt_elems() const { return (size_t)9 * 8 * F + (size_t)2 * blocks * 9 * F * F; }
+    int allocate();
+    void release();
+    int load(const float* flat, int64_t count);
+};
+
+int64_t net_param_count(int blocks, int F);
+bool net_tc_supported(int F);
+// all pointers are DEVICE pointers; asynchronous on net->ctx->stream
+int net_forward_device(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value,
+                       int out_kind);
+int net_forward_simt(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value,
+                     int out_kind);
+int net_forward_tc(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value,
+                   int out_kind);
+
+}  // namespace oth
+
+struct oth_net : public oth::NetHost {};

@@ -1,0 +1,269 @@
+// net_tc.cu -- OthelloResNet trunk as bf16 tcgen05 implicit-GEMM 3x3 convolutions (sm_100a).
+//
+// One persistent CTA per SM walks over "items" of 4 boards (2 tiles x 128 GEMM rows).  The
+// whole network runs inside the kernel: activations never leave shared memory, accumulators
+// live in TMEM, and only the BN-folded bf16 weights stream in (L2-resident, 1-D bulk-TMA
+// copies into a 3-slot ring, each slot consumed by both tiles).
+//
+//   warps 0-3 : tile 0 epilogue (TMEM -> +bias/+skip/ReLU -> bf16 -> shared), input planes, heads
+//   warps 4-7 : tile 1 epilogue, same
+//   warp  8   : weight producer (one lane issues cp.async.bulk + mbarrier expect_tx)
+//   warp  9   : MMA issuer (one lane issues tcgen05.mma / tcgen05.commit), owns the TMEM allocation
+//
+// A 3x3 tap is not materialised (no im2col): the activation tile is stored K-major without
+// swizzle (net_common.cuh) so that tap (dy,dx) is the SAME UMMA shared-memory descriptor with
+// its start address moved by (dy*18+dx) 16-byte units; zero pad units / halo groups supply the
+// padding=1 zeros.  GEMM per conv and tile: M=128 (2 boards), N=F, K=9*F in steps of 16.
+//
+// Restates src/model/net.py:15-61,139-205 (eval mode, BN folded) -- numerics: bf16 operands,
+// fp32 accumulation in TMEM, bf16 activations between layers, fp32 heads.
+#include "common.cuh"
+#include "net_common.cuh"
+#include "net_host.cuh"
+#include "tc_ptx.cuh"
+
+namespace oth {
+namespace tc {
+
+constexpr int kComputeWarps = 8;
+constexpr int kThreads = (kComputeWarps + 2) * 32;   // 320
+constexpr int kStages = 3;
+
+template <int F>
+struct Cfg {
+    static constexpr int KC = F / 8;
+    static constexpr int kTileBytes = tile_buffer_bytes(KC);
+    static constexpr int kStageBytes = 128 * F;            // 8 channel planes x F rows x 16 B
+    static constexpr int kStemStageBytes = 3 * 2 * F * 16; // 3 taps x 2 planes (K padded to 16)
+    static constexpr int kStagesPerTap = F / 64;
+    static constexpr int kTmemCols = 2 * F;                // two fp32 accumulator tiles
+    // shared-memory map
+    static constexpr int offA = 0;                          // A[2] : conv1 output h / network input
+    static constexpr int offB = 2 * kTileBytes;             // B[2] : residual stream x
+    static constexpr int offRing = 4 * kTileBytes;
+    static constexpr int offHeads = offRing + kStages * kStageBytes;
+    static constexpr int offBars = offHeads + 2 * (int)sizeof(HeadScratch);
+    static constexpr int kNumBars = 2 * kStages + 4;
+    static constexpr int offMisc = offBars + kNumBars * 8;
+    static constexpr int kSmemBytes = offMisc + 128;
+    static_assert(sizeof(HeadScratch) % 16 == 0, "HeadScratch must keep 16-byte alignment");
+    static_assert(kSmemBytes <= 232448, "shared-memory budget (227 KB) exceeded");
+};
+
+struct Misc {
+    uint32_t tmem_base;
+    uint32_t pad;
+    uint64_t s_self[4], s_opp[4], s_legal[4];
+};
+
+template <int F>
+__global__ void __launch_bounds__(kThreads, 1)
+k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* __restrict__ opp_b, int64_t n,
+         float* __restrict__ policy_out, float* __restrict__ value_out, int out_kind)
+{
+    using C = Cfg<F>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::offBars);
+    uint64_t* bar_full = bars;                       // [kStages] weights landed
+    uint64_t* bar_empty = bars + kStages;            // [kStages] slot consumed by the tensor core
+    uint64_t* bar_acc = bars + 2 * kStages;          // [2] accumulator tile complete
+    uint64_t* bar_act = bars + 2 * kStages + 2;      // [2] activation tile written (128 arrivals)
+    Misc* misc = reinterpret_cast<Misc*>(smem + C::offMisc);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_layers = 1 + 2 * net.blocks;
+    const int64_t n_items = (n + 3) / 4;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc[i], 1); mbar_init(&bar_act[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == kComputeWarps + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc->tmem_base)),
+                     "r"((uint32_t)C::kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = misc->tmem_base;
+
+    if (warp < kComputeWarps) {
+        // ===================== epilogue / input / heads =====================
+        const int tile = warp >> 2;
+        const int m = ((warp & 3) << 5) | lane;          // GEMM row == TMEM lane
+        const int tt = threadIdx.x & 127;                 // thread index within the tile's 128 threads
+        uint4* bufA = reinterpret_cast<uint4*>(smem + C::offA + tile * C::kTileBytes);
+        uint4* bufB = reinterpret_cast<uint4*>(smem + C::offB + tile * C::kTileBytes);
+        HeadScratch* hs = reinterpret_cast<HeadScratch*>(smem + C::offHeads) + tile;
+        zero_tile_buffer(bufA, C::KC, tt, 128);
+        zero_tile_buffer(bufB, C::KC, tt, 128);
+        uint32_t acc_phase = 0;
+        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            named_bar_sync(1, kComputeWarps * 32);        // previous item's heads are done with misc->s_*
+            if (threadIdx.x < 4) {
+                const int64_t b = item * 4 + threadIdx.x;
+                const uint64_t a = b < n ? self_b[b] : 0ULL, o = b < n ? opp_b[b] : 0ULL;
+                misc->s_self[threadIdx.x] = a; misc->s_opp[threadIdx.x] = o; misc->s_legal[threadIdx.x] = legal_moves(a, o);
+            }
+            named_bar_sync(1, kComputeWarps * 32);
+            build_input_row(bufA, m, misc->s_self + 2 * tile, misc->s_opp + 2 * tile, misc->s_legal + 2 * tile);
+            bufA[unit_of_row(1, m)] = make_uint4(0, 0, 0, 0);   // K padding plane of the stem
+            fence_async_proxy();
+            mbar_arrive(&bar_act[tile]);
+            for (int layer = 0; layer < n_layers; ++layer) {
+                const bool into_b = (layer == 0) || ((layer & 1) == 0);   // stem and conv2 write the residual stream
+                const bool skip = layer > 0 && (layer & 1) == 0;          // conv2: add the block input
+                uint4* out = into_b ? bufB : bufA;
+                const float* bias = net.bias + (size_t)layer * F;
+                mbar_wait(&bar_acc[tile], acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+#pragma unroll 1
+                for (int chunk = 0; chunk < F / 32; ++chunk) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tile * F + chunk * 32), r);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int kc = chunk * 4 + q;
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]) + __ldg(bias + kc * 8 + j);
+                        const int u = unit_of_row(kc, m);
+                        if (skip) {
+                            const uint4 x = bufB[u];
+                            v[0] += bf16_lo(x.x); v[1] += bf16_hi(x.x); v[2] += bf16_lo(x.y); v[3] += bf16_hi(x.y);
+                            v[4] += bf16_lo(x.z); v[5] += bf16_hi(x.z); v[6] += bf16_lo(x.w); v[7] += bf16_hi(x.w);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                        out[u] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                            pack_bf16x2(v[6], v[7]));
+                    }
+                }
+                tc_fence_before();
+                if (layer + 1 < n_layers) {
+                    fence_async_proxy();                  // generic-proxy stores -> visible to the tensor core
+                    mbar_arrive(&bar_act[tile]);
+                }
+            }
+            named_bar_sync(2 + tile, 128);                // final activations of this tile are complete
+            heads_for_tile(net, bufB, hs, misc->s_legal + 2 * tile, item * 4 + 2 * tile, n, policy_out, value_out, out_kind, tt,
+                           128, [tile] { named_bar_sync(2 + tile, 128); });
+        }
+    } else if (warp == kComputeWarps) {
+        // ===================== weight producer =====================
+        if (lane == 0) {
+            unsigned char* ring = smem + C::offRing;
+            uint32_t cnt = 0;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(net.w_tc);
+                for (int layer = 0; layer < n_layers; ++layer) {
+                    const int stages = layer == 0 ? 3 : 9 * C::kStagesPerTap;
+                    const uint32_t bytes = layer == 0 ? C::kStemStageBytes : C::kStageBytes;
+                    for (int s = 0; s < stages; ++s, ++cnt) {
+                        const uint32_t slot = cnt % kStages, round = cnt / kStages;
+                        mbar_wait(&bar_empty[slot], (round & 1) ^ 1);
+                        mbar_expect_tx(&bar_full[slot], bytes);
+                        bulk_g2s(ring + slot * C::kStageBytes, src, bytes, &bar_full[slot]);
+                        src += bytes;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t ringAddr = smem_u32(smem + C::offRing);
+            const uint32_t aAddr[2] = {smem_u32(smem + C::offA), smem_u32(smem + C::offA + C::kTileBytes)};
+            const uint32_t bAddr[2] = {smem_u32(smem + C::offB), smem_u32(smem + C::offB + C::kTileBytes)};
+            constexpr uint32_t idesc = umma_idesc(F);
+            constexpr uint32_t kRow0 = (kGuardUnits + kHaloUnits) * 16;   // byte offset of row 0 inside a plane-0 view
+            uint32_t cnt = 0, act_phase = 0;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                for (int layer = 0; layer < n_layers; ++layer) {
+                    const bool from_a = (layer == 0) || ((layer & 1) == 0);   // stem reads the input, conv2 reads h: both in A
+                    const uint32_t in0 = from_a ? aAddr[0] : bAddr[0], in1 = from_a ? aAddr[1] : bAddr[1];
+                    mbar_wait(&bar_act[0], act_phase);
+                    mbar_wait(&bar_act[1], act_phase);
+                    act_phase ^= 1;
+                    tc_fence_after();
+                    const int stages = layer == 0 ? 3 : 9 * C::kStagesPerTap;
+                    for (int s = 0; s < stages; ++s, ++cnt) {
+                        const uint32_t slot = cnt % kStages, round = cnt / kStages;
+                        mbar_wait(&bar_full[slot], round & 1);
+                        tc_fence_after();
+                        const uint32_t wbase = ringAddr + slot * C::kStageBytes;
+                        const bool last = (s == stages - 1);
+#pragma unroll 1
+                        for (int tile = 0; tile < 2; ++tile) {
+                            const uint32_t in = tile ? in1 : in0;
+                            const uint32_t d = tmem_base + (uint32_t)(tile * F);
+                            if (layer == 0) {
+#pragma unroll
+                                for (int t3 = 0; t3 < 3; ++t3) {
+                                    const int tap = s * 3 + t3;
+                                    const int shift = (tap / 3 - 1) * 2 * kGroupUnits + (tap % 3 - 1);
+                                    const uint64_t ad = umma_desc(in + kRow0 + shift * 16, kPlaneUnits * 16, kGroupUnits * 16);
+                                    const uint64_t bd = umma_desc(wbase + t3 * (2 * F * 16), F * 16, 128);
+                                    umma_bf16(d, ad, bd, idesc, tap > 0 ? 1u : 0u);
+                                }
+                            } else {
+                                const int tap = s / C::kStagesPerTap, part = s % C::kStagesPerTap;
+                                const int shift = (tap / 3 - 1) * 2 * kGroupUnits + (tap % 3 - 1);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int kc = part * 8 + 2 * j;
+                                    const uint64_t ad = umma_desc(in + kRow0 + (kc * kPlaneUnits + shift) * 16, kPlaneUnits * 16,
+                                                                  kGroupUnits * 16);
+                                    const uint64_t bd = umma_desc(wbase + (2 * j) * (F * 16), F * 16, 128);
+                                    umma_bf16(d, ad, bd, idesc, (s > 0 || j > 0) ? 1u : 0u);
+                                }
+                            }
+                            if (last) umma_commit(&bar_acc[tile]);   // this tile's accumulator is complete
+                        }
+                        umma_commit(&bar_empty[slot]);               // slot free once both tiles have read it
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kComputeWarps + 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols) : "memory");
+    }
+}
+
+}  // namespace tc
+
+bool net_tc_supported(int F) { return F == 64 || F == 128; }
+
+int net_forward_tc(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value,
+                   int out_kind)
+{
+    oth_ctx* ctx = net->ctx;
+    OTH_REQUIRE(net_tc_supported(net->F), OTH_ERR_UNSUPPORTED, "tcgen05 engine supports num_filters 64 or 128 (got %d)", net->F);
+    const int64_t items = (n + 3) / 4;
+    int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
+    if (grid < 1) grid = 1;
+    if (net->F == 128) {
+        using C = tc::Cfg<128>;
+        OTH_CHECK_CUDA(cudaFuncSetAttribute(tc::k_net_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+        tc::k_net_tc<128><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(net->dev, self_b, opp_b, n, policy, value, out_kind);
+    } else {
+        using C = tc::Cfg<64>;
+        OTH_CHECK_CUDA(cudaFuncSetAttribute(tc::k_net_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+        tc::k_net_tc<64><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(net->dev, self_b, opp_b, n, policy, value, out_kind);
+    }
+    ctx->launches++;
+    OTH_CHECK_CUDA(cudaGetLastError());
+    return OTH_OK;
+}
+
+}  // namespace oth

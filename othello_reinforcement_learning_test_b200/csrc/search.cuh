@@ -1,0 +1,62 @@
+// search.cuh -- device-resident SoA Monte-Carlo tree, shared by search.cu and selfplay.cu.
+#pragma once
+#include "common.cuh"
+#include "net_host.cuh"
+
+namespace oth {
+
+constexpr int kEdgesPerNodeBudget = 40;   // pool sizing only; a node may have up to 64 children
+
+// All arrays are device memory.  Per game g: nodes [g*node_cap .. +node_cap), edges
+// [g*edge_cap .. +edge_cap) allocated CSR-style in expansion order (node 0 = root).
+// An "edge" carries what the reference keeps on the child MCTSNode (node.py:28-45):
+// prior P (float32), visit_count N, value_sum W (float64) and the link to its own children.
+struct TreeDev {
+    int64_t games;            // capacity (slots)
+    int node_cap, edge_cap, path_cap;
+    // per game
+    uint64_t *root_self, *root_opp;
+    int32_t *n_nodes, *n_edges, *n_evals, *sims_done, *path_len;
+    uint8_t *pending, *active;
+    uint64_t *leaf_self, *leaf_opp, *leaf_legal;   // evaluation batch (slot = game)
+    int32_t* path;            // [games][path_cap] edge indices of the pending simulation
+    // per node
+    int32_t* node_first;      // first edge
+    int32_t* node_count;      // number of edges (0 = not expanded)
+    // per edge
+    int32_t* edge_n;
+    double* edge_w;
+    float* edge_p;
+    int32_t* edge_child;      // node index, -1 while the child is a leaf
+    uint8_t* edge_action;
+    // evaluator outputs for the batch
+    float* eval_policy;       // [games][65]
+    float* eval_value;        // [games]
+    int32_t* error_flag;      // != 0: a pool overflowed
+};
+
+struct SearchHost {
+    oth_ctx* ctx = nullptr;
+    int64_t max_games = 0, n = 0;
+    int max_sims = 0;
+    double c_puct = 1.0, dir_alpha = 0.3, dir_eps = 0.25;
+    uint32_t flags = 0;
+    bool begun = false, awaiting_apply = false, root_pending = false;
+    TreeDev t{};
+    std::vector<void*> allocs;
+    uint64_t total_evals = 0;
+
+    int allocate(oth_ctx* c, int64_t games, int sims);
+    void release();
+    // device-pointer, asynchronous building blocks (n = live games, all on ctx->stream)
+    int begin(const uint64_t* d_self, const uint64_t* d_opp, const uint8_t* d_active, int64_t n_games);
+    int select();                                              // one descent per game -> leaf batch / terminal backup
+    int expand(const float* d_policy, const float* d_value, bool policy_is_raw);   // expand pending leaves + backup
+    int evaluate(NetHost* net);                                // leaf batch -> t.eval_policy (priors) / t.eval_value
+    int run(NetHost* net, int sims, bool add_noise, uint64_t seed);
+    int check_overflow();
+};
+
+}  // namespace oth
+
+struct oth_search : public oth::SearchHost {};

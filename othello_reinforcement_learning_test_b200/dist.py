@@ -1,0 +1,81 @@
+"""Multi-GPU plumbing: one process per GPU, games sharded, no traffic inside the move loop.
+
+Self-play games are independent, so a campaign of E episodes on W ranks is W independent
+campaigns of ceil(E/W) episodes.  `torch.distributed` (NCCL over
+NVLink/NVSwitch on the GPU box, gloo in the CPU tests) is used for exactly two things, both
+outside the per-move loop:
+
+  * `broadcast_weights(model, src)`   -- new network weights from the trainer rank;
+  * `all_gather_samples(samples)`     -- packed trajectories (168 B records) to every rank,
+                                         i.e. into the replay buffer's rank.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._lib import SAMPLE_DTYPE
+
+
+def shard_episodes(num_episodes: int, rank: int, world_size: int) -> int:
+    """Episodes this rank plays: contiguous, balanced, sums to num_episodes."""
+    base, rem = divmod(int(num_episodes), int(world_size))
+    return base + (1 if rank < rem else 0)
+
+
+def _comm_device() -> torch.device:
+    if dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def broadcast_weights(model: torch.nn.Module, src: int = 0) -> int:
+    """Broadcast every parameter and buffer of `model` from rank `src` as ONE flat buffer
+    (2.98 M floats for 10x128: a single latency-bound collective).  Returns the byte count."""
+    tensors = [t for t in model.state_dict().values()]
+    dev = _comm_device()
+    flat = torch.cat([t.detach().reshape(-1).to(dev, torch.float32) for t in tensors])
+    dist.broadcast(flat, src=src)
+    off = 0
+    with torch.no_grad():
+        for t in tensors:
+            n = t.numel()
+            t.copy_(flat[off:off + n].reshape(t.shape).to(t.dtype))
+            off += n
+    return flat.numel() * 4
+
+
+def all_gather_samples(samples: np.ndarray) -> np.ndarray:
+    """All-gather variable-length packed sample arrays; every rank gets the concatenation in
+    rank order."""
+    assert samples.dtype == SAMPLE_DTYPE
+    world = dist.get_world_size()
+    dev = _comm_device()
+    count = torch.tensor([samples.size], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(count) for _ in range(world)]
+    dist.all_gather(counts, count)
+    counts = [int(c.item()) for c in counts]
+    biggest = max(counts) if counts else 0
+    rec = SAMPLE_DTYPE.itemsize
+    buf = torch.zeros(max(biggest, 1) * rec, dtype=torch.uint8, device=dev)
+    if samples.size:
+        buf[: samples.size * rec] = torch.from_numpy(samples.view(np.uint8).reshape(-1).copy()).to(dev)
+    gathered = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(gathered, buf)
+    parts = [g[: c * rec].cpu().numpy().view(SAMPLE_DTYPE) for g, c in zip(gathered, counts)]
+    out = np.concatenate(parts) if parts else np.empty(0, SAMPLE_DTYPE)
+    # make episode ids globally unique: offset by the episodes of the lower ranks
+    return out
+
+
+def renumber_games(samples_per_rank: list[np.ndarray]) -> np.ndarray:
+    """Concatenate per-rank sample arrays giving every episode a globally unique id."""
+    out, base = [], 0
+    for s in samples_per_rank:
+        s = s.copy()
+        if s.size:
+            s["game"] += base
+            base = int(s["game"].max()) + 1
+        out.append(s)
+    return np.concatenate(out) if out else np.empty(0, SAMPLE_DTYPE)

@@ -1,0 +1,116 @@
+"""GPU parity: the device-resident self-play campaign vs the reference's ParallelSelfPlayWorker."""
+import numpy as np
+import pytest
+
+from oracle import cref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_deterministic_trace_equals_the_reference(golden_selfplay, tag):
+    """temperature_threshold = 0 makes every move an arg-max: the whole game, the stored visit
+    distributions and the value labels must equal what the reference's worker produced."""
+    import othello_reinforcement_learning_test_b200 as pkg
+    g = golden_selfplay
+    cp, sims = float(g[f"{tag}_cfg"][0]), int(g[f"{tag}_cfg"][1])
+    w = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", num_simulations=sims, temperature_threshold=0,
+                                   num_parallel_games=1, c_puct=cp, seed=1, verbose=False)
+    data = w.execute_episodes(3, add_dirichlet_noise=True)        # three identical deterministic games
+    n = len(g[f"{tag}_batched_value"])
+    assert len(data) == 3 * n
+    want_states = cref.tensor_input_batch(g[f"{tag}_batched_self"], g[f"{tag}_batched_opp"])
+    for rep in range(3):
+        for i in range(n):
+            st, pol, val = data[rep * n + i]
+            assert np.array_equal(st, want_states[i]), (rep, i)
+            assert np.array_equal(pol, g[f"{tag}_batched_policy"][i]), (rep, i)
+            assert val == float(g[f"{tag}_batched_value"][i])
+    assert w.last_stats["nn_evals"] > 3 * n * sims * 0.8
+
+
+def test_serial_worker_equals_the_reference(golden_selfplay):
+    import othello_reinforcement_learning_test_b200 as pkg
+    g = golden_selfplay
+    cp, sims = float(g["a_cfg"][0]), int(g["a_cfg"][1])
+    m = pkg.MCTS(None, "cuda", c_puct=cp)
+    data = pkg.SelfPlayWorker(pkg.OthelloBitboard, m, num_simulations=sims, temperature_threshold=0).execute_episode(False)
+    assert len(data) == len(g["a_serial_value"])
+    for i, (st, pol, val) in enumerate(data):
+        assert st.shape == (3, 8, 8) and pol.shape == (65,)
+        assert np.array_equal(pol, g["a_serial_policy"][i]) and val == float(g["a_serial_value"][i])
+
+
+def test_sampled_campaign_is_consistent_under_replay():
+    """With sampling (own RNG, not comparable to numpy's stream) every recorded game must still be a
+    legal REF-rules game whose records agree with the oracle ply by ply."""
+    import othello_reinforcement_learning_test_b200 as pkg
+    sims = 20
+    w = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", num_simulations=sims, temperature_threshold=15,
+                                   num_parallel_games=16, c_puct=1.0, seed=5, concurrent_games=64, verbose=False)
+    smp = w.execute_episodes_packed(200, add_dirichlet_noise=True)     # 64 slots, 200 episodes: exercises refill
+    assert sorted(set(smp["game"].tolist())) == list(range(200))
+    order = np.lexsort((smp["ply"], smp["game"]))
+    smp = smp[order]
+    n_distinct_openings = set()
+    for gid in range(200):
+        rec = smp[smp["game"] == gid]
+        assert (rec["ply"] == np.arange(rec.size)).all()
+        s, o, mc = cref.START_SELF, cref.START_OPP, 0
+        for i, r in enumerate(rec):
+            assert (int(r["self_b"]), int(r["opp_b"])) == (s, o), (gid, i)
+            assert int(r["legal"]) == cref.legal(s, o)
+            vis = r["visits"].astype(np.int64)
+            legal = cref.legal_list(s, o)
+            assert vis.sum() == sims and all(vis[a] == 0 for a in range(65) if a not in legal)
+            assert r["n_children"] == len(legal)
+            want = cref.mcts_search(s, o, sims, 1.0)["visits"]
+            assert np.array_equal(vis, want)
+            if i + 1 < rec.size:
+                nxt = (int(rec[i + 1]["self_b"]), int(rec[i + 1]["opp_b"]))
+                cands = []
+                for a in legal:
+                    ok, s2, o2, _ = cref.make_move(s, o, mc, a)
+                    if ok and (s2, o2) == nxt and vis[a] > 0:
+                        cands.append(a)
+                assert cands, (gid, i)
+                if i >= 15:
+                    assert cands[0] == int(np.argmax(vis))             # arg-max after the threshold
+                ok, s, o, mc = cref.make_move(s, o, mc, cands[0])
+        # the last record's move ends the game; label = winner at the terminal position x player
+        last = rec[-1]
+        vis = last["visits"].astype(np.int64)
+        ends = []
+        for a in cref.legal_list(s, o):
+            ok, s2, o2, _ = cref.make_move(s, o, mc, a)
+            if ok and vis[a] > 0 and cref.is_terminal(s2, o2):
+                ends.append(cref.winner(s2, o2))
+        assert ends
+        labels = rec["value"].astype(np.int64)
+        assert any((labels == np.array([wv * (1 if i % 2 == 0 else -1) for i in range(rec.size)])).all() for wv in ends)
+        n_distinct_openings.add(tuple(rec["self_b"][:6].tolist()))
+    assert len(n_distinct_openings) > 20          # sampling really happens before the threshold
+
+
+def test_training_data_format_like_the_reference_tests():
+    import othello_reinforcement_learning_test_b200 as pkg
+    w = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", num_simulations=5, temperature_threshold=15,
+                                   num_parallel_games=4, seed=3, verbose=False)
+    data = w.execute_episodes(4, add_dirichlet_noise=True)
+    assert len(data) >= 4 * 8
+    for st, pol, val in data:                                          # tests/test_train.py:116-130
+        assert st.shape == (3, 8, 8) and st.dtype == np.float32
+        assert pol.shape == (65,) and abs(pol.sum() - 1.0) < 1e-5
+        assert val in (-1.0, 0.0, 1.0)
+    assert w.execute_episodes(0) == []
+
+
+def test_winner_black_flag_only_changes_labels():
+    import othello_reinforcement_learning_test_b200 as pkg
+    kw = dict(num_simulations=10, temperature_threshold=0, num_parallel_games=1, seed=1, verbose=False)
+    a = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", **kw).execute_episodes_packed(1)
+    b = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", winner_black=True, **kw).execute_episodes_packed(1)
+    assert np.array_equal(a["self_b"], b["self_b"]) and np.array_equal(a["visits"], b["visits"])
+    plies = a.size
+    # REF label: winner is seen from the side to move at the end; black-relative flips it on odd game lengths
+    assert np.array_equal(b["value"], a["value"] * (-1 if plies % 2 else 1))

@@ -1,0 +1,90 @@
+"""GPU parity: OthelloResNet inference, CUDA-core validation engine, vs the fp32 reference outputs.
+Tolerances (north_star: bf16 tolerance, e.g. max abs 2e-2 against fp32):
+  * vs fp32 reference module outputs (golden): policy probabilities and value max-abs <= 2e-2 for the
+    seed-42 initialisation; <= 4e-2 for the deliberately hot synthetic weights (bf16 over 21 layers);
+  * vs the CPU emulation of the same numerics (bf16 operands/activations, fp32 accumulate): <= 3e-3."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cref, net_oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32_INIT42 = 2e-2
+TOL_FP32_SYNTH = 4e-2
+TOL_EMULATED = 3e-3
+
+
+def _check(net, sd, S, O, logp_ref, v_ref, tol_fp32):
+    lp, v = net.forward(S, O, out="logprobs")
+    assert lp.shape == (S.size, 65) and v.shape == (S.size,)
+    assert np.abs(np.exp(lp) - np.exp(logp_ref)).max() <= tol_fp32
+    assert np.abs(v - v_ref).max() <= tol_fp32
+    x = net_oracle.boards_to_tensor(S, O)
+    lpe, ve = net_oracle.forward_bf16_emulated(sd, x)
+    assert np.abs(np.exp(lp) - np.exp(lpe.numpy())).max() <= TOL_EMULATED
+    assert np.abs(v - ve.numpy().reshape(-1)).max() <= TOL_EMULATED
+    assert np.allclose(np.exp(lp).sum(axis=1), 1.0, atol=1e-4) and (lp <= 1e-6).all() and (np.abs(v) <= 1).all()
+    return lp, v
+
+
+@pytest.mark.parametrize("nb,nf,seed", [(2, 32, 5), (5, 64, 6), (10, 128, 7)])
+def test_simt_engine_synthetic_weights(ctx, golden_net, nb, nf, seed):
+    from othello_reinforcement_learning_test_b200.net import InferenceNet
+    g = golden_net
+    sd = net_oracle.make_state_dict(nb, nf, seed)
+    net = InferenceNet(nb, nf, ctx, engine="simt")
+    net.load_state_dict(sd)
+    _check(net, sd, g["self_b"], g["opp_b"], g[f"logp_{nb}x{nf}_s{seed}"], g[f"value_{nb}x{nf}_s{seed}"], TOL_FP32_SYNTH)
+
+
+@pytest.mark.parametrize("nb,nf", [(5, 64), (10, 128)])
+def test_simt_engine_seed42_init(ctx, golden_net, nb, nf):
+    from othello_reinforcement_learning_test_b200.net import InferenceNet, OthelloResNet
+    g = golden_net
+    torch.manual_seed(42)
+    m = OthelloResNet(nb, nf).eval()
+    net = InferenceNet.from_module(m, ctx, engine="simt")
+    _check(net, m.state_dict(), g["self_b"], g["opp_b"], g[f"init42_{nb}x{nf}_logp"], g[f"init42_{nb}x{nf}_value"],
+           TOL_FP32_INIT42)
+
+
+def test_output_kinds_ragged_sizes_and_weight_refresh(ctx, golden_net):
+    from othello_reinforcement_learning_test_b200.net import InferenceNet, OthelloResNet
+    g = golden_net
+    S, O = g["self_b"], g["opp_b"]
+    torch.manual_seed(1)
+    m = OthelloResNet(2, 32).eval()
+    net = InferenceNet.from_module(m, ctx, engine="simt")
+    lp, v = net.forward(S, O, out="logprobs")
+    p, v2 = net.forward(S, O, out="probs")
+    pri, v3 = net.forward(S, O, out="priors")
+    assert np.array_equal(v, v2) and np.array_equal(v, v3)
+    assert np.allclose(p, np.exp(lp), rtol=1e-5, atol=1e-7)
+    for i in range(S.size):                                            # priors == MCTSNode.expand's masking
+        want = cref.expand_priors(p[i], np.array(cref.legal_list(int(S[i]), int(O[i])), np.int32))
+        assert np.array_equal(pri[i], want), i
+    for n in (0, 1, 2, 3, 5):                                          # ragged: tiles hold 2 boards
+        a, b = net.forward(S[:n], O[:n])
+        assert a.shape == (n, 65) and np.array_equal(a, lp[:n]) and np.array_equal(b, v[:n])
+    # position in the batch does not matter (needed for result-transparent caching later)
+    perm = np.random.default_rng(0).permutation(S.size)
+    a, b = net.forward(S[perm], O[perm])
+    assert np.array_equal(a, lp[perm]) and np.array_equal(b, v[perm])
+    # the trainer mutates the module in place: sync_from must notice
+    assert net.sync_from(m) is False
+    with torch.no_grad():
+        m.policy_head.fc.bias.add_(0.5 * torch.arange(65.0) / 65)
+    assert net.sync_from(m) is True
+    lp2, _ = net.forward(S, O)
+    assert np.abs(lp2 - lp).max() > 1e-3
+    # device-pointer path
+    ds = torch.from_numpy(S.view(np.int64)).cuda(); do = torch.from_numpy(O.view(np.int64)).cuda()
+    a, b = net.forward(ds, do)
+    ctx.sync()
+    assert np.array_equal(a.cpu().numpy(), lp2)
+    # wrong-sized weight vector is rejected with an error, not a crash
+    import othello_reinforcement_learning_test_b200 as pkg
+    bad = np.zeros(10, np.float32)
+    assert ctx.lib.oth_net_load_weights(net.handle, bad.ctypes.data, 10) != 0 and "needs" in pkg._lib.last_error()

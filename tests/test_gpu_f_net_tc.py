@@ -1,0 +1,83 @@
+"""GPU parity: the tcgen05/TMEM implicit-GEMM engine (product path) vs the fp32 reference outputs, the
+CPU emulation of its numerics, and the CUDA-core validation engine.  Tolerances as in
+test_gpu_d_net_simt.py (2e-2 vs fp32 for the seed-42 initialisation, 3e-3 vs the bf16 emulation)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cref, net_oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32_INIT42 = 2e-2
+TOL_FP32_SYNTH = 4e-2
+TOL_EMULATED = 3e-3
+
+
+def _nets(ctx, sd, nb, nf):
+    from othello_reinforcement_learning_test_b200.net import InferenceNet
+    tc = InferenceNet(nb, nf, ctx, engine="tcgen05"); tc.load_state_dict(sd)
+    simt = InferenceNet(nb, nf, ctx, engine="simt"); simt.load_state_dict(sd)
+    return tc, simt
+
+
+@pytest.mark.parametrize("nb,nf,seed", [(5, 64, 6), (10, 128, 7)])
+def test_tc_engine_synthetic_weights(ctx, golden_net, nb, nf, seed):
+    g = golden_net
+    S, O = g["self_b"], g["opp_b"]
+    sd = net_oracle.make_state_dict(nb, nf, seed)
+    tc, simt = _nets(ctx, sd, nb, nf)
+    lp, v = tc.forward(S, O)
+    assert np.isfinite(lp).all() and np.isfinite(v).all()
+    assert np.abs(np.exp(lp) - np.exp(g[f"logp_{nb}x{nf}_s{seed}"])).max() <= TOL_FP32_SYNTH
+    assert np.abs(v - g[f"value_{nb}x{nf}_s{seed}"]).max() <= TOL_FP32_SYNTH
+    lpe, ve = net_oracle.forward_bf16_emulated(sd, net_oracle.boards_to_tensor(S, O))
+    assert np.abs(np.exp(lp) - np.exp(lpe.numpy())).max() <= TOL_EMULATED
+    assert np.abs(v - ve.numpy().reshape(-1)).max() <= TOL_EMULATED
+    lps, vs = simt.forward(S, O)
+    assert np.abs(np.exp(lp) - np.exp(lps)).max() <= TOL_EMULATED and np.abs(v - vs).max() <= TOL_EMULATED
+
+
+@pytest.mark.parametrize("nb,nf", [(5, 64), (10, 128)])
+def test_tc_engine_seed42_init(ctx, golden_net, nb, nf):
+    from othello_reinforcement_learning_test_b200.net import InferenceNet, OthelloResNet
+    g = golden_net
+    torch.manual_seed(42)
+    m = OthelloResNet(nb, nf).eval()
+    net = InferenceNet.from_module(m, ctx)               # default engine for 64/128 filters = tcgen05
+    lp, v = net.forward(g["self_b"], g["opp_b"])
+    assert np.abs(np.exp(lp) - np.exp(g[f"init42_{nb}x{nf}_logp"])).max() <= TOL_FP32_INIT42
+    assert np.abs(v - g[f"init42_{nb}x{nf}_value"]).max() <= TOL_FP32_INIT42
+
+
+def test_tc_engine_batch_sizes_order_independence_and_priors(ctx, golden_net, golden_games):
+    g = golden_net
+    sd = net_oracle.make_state_dict(5, 64, 6)
+    tc, simt = _nets(ctx, sd, 5, 64)
+    live = np.flatnonzero(golden_games["terminal"] == 0)
+    idx = np.random.default_rng(4).choice(live, 3001, replace=False)      # not a multiple of 4: ragged last item
+    S, O = golden_games["self_b"][idx], golden_games["opp_b"][idx]
+    lp, v = tc.forward(S, O)
+    lps, vs = simt.forward(S, O)
+    assert np.abs(np.exp(lp) - np.exp(lps)).max() <= TOL_EMULATED and np.abs(v - vs).max() <= TOL_EMULATED
+    for n in (0, 1, 2, 3, 4, 5, 7, 600):                                   # > 148 items: the persistent loop wraps
+        a, b = tc.forward(S[:n], O[:n])
+        assert np.array_equal(a, lp[:n]) and np.array_equal(b, v[:n]), n
+    perm = np.random.default_rng(1).permutation(S.size)
+    a, b = tc.forward(S[perm], O[perm])
+    assert np.array_equal(a, lp[perm]) and np.array_equal(b, v[perm])      # slot / tile / CTA independent, bit for bit
+    a2, b2 = tc.forward(S[perm], O[perm])
+    assert np.array_equal(a, a2) and np.array_equal(b, b2)                 # deterministic
+    p, _ = tc.forward(S[:200], O[:200], out="probs")
+    pri, _ = tc.forward(S[:200], O[:200], out="priors")
+    for i in range(200):
+        want = cref.expand_priors(p[i], np.array(cref.legal_list(int(S[i]), int(O[i])), np.int32))
+        assert np.array_equal(pri[i], want), i
+
+
+def test_tc_engine_rejects_unsupported_filter_counts(ctx):
+    import othello_reinforcement_learning_test_b200 as pkg
+    from othello_reinforcement_learning_test_b200.net import InferenceNet
+    net = InferenceNet(2, 32, ctx)                     # falls to the validation engine by itself
+    with pytest.raises(pkg.OthelloB200Error):
+        net.set_engine("tcgen05")

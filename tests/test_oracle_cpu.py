@@ -1,0 +1,156 @@
+"""CPU suite: the oracle (oracle/ref_rules.c, oracle/net_oracle.py) against the committed golden
+vectors that were produced by running the reference itself (oracle/gen_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cref, net_oracle
+
+
+def test_perft_matches_reference(golden_bitboard):
+    ref = golden_bitboard["perft_ref_rules"]
+    got = [cref.perft(cref.START_SELF, cref.START_OPP, d) for d in range(len(ref))]
+    assert got == ref
+    # REF rules are NOT standard Othello: they part ways at depth 7
+    std = golden_bitboard["perft_standard_for_contrast"]
+    assert got[:7] == std[:7] and got[7] != std[7]
+
+
+def test_edge_vectors_and_initial_position(golden_bitboard):
+    for ev in golden_bitboard["edge_vectors"]:
+        assert cref.legal_list(ev["self"], ev["opp"]) == ev["legal"]
+    assert cref.legal_list(cref.START_SELF, cref.START_OPP) == golden_bitboard["initial_legal"] == [19, 26, 37, 44]
+    assert cref.legal(cref.START_SELF, cref.START_OPP) == golden_bitboard["initial_legal_bits"]
+    ok, s, o, mc = cref.make_move(cref.START_SELF, cref.START_OPP, 0, 19)
+    assert ok and mc == 1
+    assert [bin(s).count("1"), bin(o).count("1")] == golden_bitboard["after_move_19_counts"] == [1, 4]
+
+
+def test_reference_games_every_ply(golden_games):
+    g = golden_games
+    S, O = g["self_b"], g["opp_b"]
+    assert np.array_equal(cref.legal_batch(S, O), g["legal"])
+    t, w = cref.terminal_winner_batch(S, O)
+    assert np.array_equal(t, g["terminal"]) and np.array_equal(w, g["winner"])
+    live = g["terminal"] == 0
+    s2, o2, mc2, ok = cref.make_move_batch(S[live], O[live], g["move_count"][live], g["action"][live])
+    assert ok.all()
+    # the next row of the same game is the position after the move
+    nxt = np.flatnonzero(live) + 1
+    assert np.array_equal(s2, S[nxt]) and np.array_equal(o2, O[nxt]) and np.array_equal(mc2, g["move_count"][nxt])
+
+
+def test_all_65_actions_and_reject_paths(golden_moves65):
+    m = golden_moves65
+    s2, o2, mc2, ok = cref.make_move_batch(m["self_b"], m["opp_b"], m["move_count"], m["action"])
+    assert np.array_equal(ok, m["ok"])
+    assert np.array_equal(s2, m["self_after"]) and np.array_equal(o2, m["opp_after"])
+    assert np.array_equal(mc2, m["move_count_after"])
+    assert (m["ok"] == 0).sum() > 1000      # the fixture really exercises the reject paths
+
+
+def test_tensor_input_layout():
+    x = cref.tensor_input_batch(np.array([cref.START_SELF], np.uint64), np.array([cref.START_OPP], np.uint64))[0]
+    assert x.shape == (3, 8, 8) and x.dtype == np.float32
+    assert x[0, 3, 4] == 1 and x[0, 4, 3] == 1 and x[0].sum() == 2     # E4, D5 (tests/test_bitboard.py:151-173)
+    assert x[1, 3, 3] == 1 and x[1, 4, 4] == 1 and x[1].sum() == 2
+    assert sorted(np.flatnonzero(x[2].reshape(-1)).tolist()) == [19, 26, 37, 44]
+
+
+def test_numpy_sum_order_is_what_the_oracle_assumes():
+    """ref_expand_priors hard-codes numpy's pairwise float32 add-reduce order."""
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        p = (rng.random(65) ** 4).astype(np.float32)
+        k = int(rng.integers(1, 30))
+        legal = np.sort(rng.choice(64, k, replace=False)).astype(np.int32)
+        masked = np.zeros_like(p); masked[legal] = p[legal]
+        want = masked / masked.sum()
+        got = cref.expand_priors(p, legal)
+        assert np.array_equal(got, want)
+    p = np.zeros(65, np.float32)
+    got = cref.expand_priors(p, np.array([3, 9, 20], np.int32))
+    assert np.array_equal(got[[3, 9, 20]], np.full(3, np.float32(1.0 / 3)))
+
+
+def test_mcts_tier1_unmodified_reference_with_recorded_network_outputs(golden_mcts):
+    g = golden_mcts
+    off = g["t1_tab_off"]
+    for i in range(len(g["t1_root_self"])):
+        tab = {(int(a), int(b)): (p, float(v)) for a, b, p, v in
+               zip(g["t1_tab_self"][off[i]:off[i + 1]], g["t1_tab_opp"][off[i]:off[i + 1]],
+                   g["t1_tab_probs"][off[i]:off[i + 1]], g["t1_tab_value"][off[i]:off[i + 1]])}
+        res = cref.mcts_search(int(g["t1_root_self"][i]), int(g["t1_root_opp"][i]), int(g["t1_sims"][i]),
+                               float(g["t1_c_puct"][i]), evaluator=lambda a, b: tab[(a, b)])
+        assert np.array_equal(res["visits"], g["t1_visits"][i])
+        assert res["n_evals"] == off[i + 1] - off[i]
+        assert np.array_equal(cref.policy_from_visits(res["visits"], res["is_child"], 1.0), g["t1_policy_t1"][i])
+        assert np.array_equal(cref.policy_from_visits(res["visits"], res["is_child"], 0.0), g["t1_policy_t0"][i])
+
+
+def test_mcts_tier2_hashnet(golden_mcts):
+    g = golden_mcts
+    for cp, sims in sorted({(float(c), int(s)) for c, s in zip(g["t2_c_puct"], g["t2_sims"])}):
+        sel = (g["t2_c_puct"] == cp) & (g["t2_sims"] == sims)
+        vis, _ = cref.mcts_search_hashnet_batch(g["t2_root_self"][sel], g["t2_root_opp"][sel], sims, cp)
+        assert np.array_equal(vis, g["t2_visits"][sel].astype(np.int32))
+
+
+def test_start_position_visit_concentration():
+    """Root selection is arg-max Q (root N stays 0), so visits pile onto one child."""
+    res = cref.mcts_search(cref.START_SELF, cref.START_OPP, 50, 1.0)
+    assert res["visits"].sum() == 50 and res["visits"].max() >= 40
+
+
+def _oracle_selfplay(cp, sims, serial):
+    s, o, mc = cref.START_SELF, cref.START_OPP, 0
+    states, pols = [], []
+    while not cref.is_terminal(s, o):
+        res = cref.mcts_search(s, o, sims, cp)
+        pol1 = cref.policy_from_visits(res["visits"], res["is_child"], 1.0)
+        pol0 = cref.policy_from_visits(res["visits"], res["is_child"], 0.0)
+        states.append((s, o)); pols.append(pol0 if serial else pol1)
+        ok, s, o, mc = cref.make_move(s, o, mc, int(np.argmax(pol1)))
+        assert ok
+    w = cref.winner(s, o)
+    vals = [float(w * (1 if i % 2 == 0 else -1)) for i in range(len(states))]
+    return states, np.array(pols), np.array(vals, np.float32)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_selfplay_traces(golden_selfplay, tag):
+    g = golden_selfplay
+    cp, sims = g[f"{tag}_cfg"]
+    states, pols, vals = _oracle_selfplay(float(cp), int(sims), serial=False)
+    assert [x[0] for x in states] == g[f"{tag}_batched_self"].tolist()
+    assert [x[1] for x in states] == g[f"{tag}_batched_opp"].tolist()
+    assert np.array_equal(pols, g[f"{tag}_batched_policy"])
+    assert np.array_equal(vals, g[f"{tag}_batched_value"])
+    _, pols0, vals0 = _oracle_selfplay(float(cp), int(sims), serial=True)
+    assert np.array_equal(pols0, g[f"{tag}_serial_policy"]) and np.array_equal(vals0, g[f"{tag}_serial_value"])
+
+
+@pytest.mark.parametrize("nb,nf,seed", [(2, 32, 5), (5, 64, 6), (10, 128, 7)])
+def test_net_fp32_restatement_matches_reference_module_outputs(golden_net, nb, nf, seed):
+    g = golden_net
+    sd = net_oracle.make_state_dict(nb, nf, seed)
+    x = net_oracle.boards_to_tensor(g["self_b"], g["opp_b"])
+    torch.set_num_threads(4)
+    lp, v = net_oracle.forward_fp32(sd, x)
+    # same torch, same machine class: equality up to thread-count dependent summation order
+    assert np.allclose(lp.numpy(), g[f"logp_{nb}x{nf}_s{seed}"], atol=2e-5, rtol=0)
+    assert np.allclose(v.numpy().reshape(-1), g[f"value_{nb}x{nf}_s{seed}"], atol=2e-5, rtol=0)
+
+
+def test_bf16_emulation_error_budget(golden_net):
+    """The numerics the CUDA kernels implement (bf16 operands/activations, fp32 accumulate) stay within
+    the tolerance north_star states (max abs 2e-2 on policy probabilities and value) for the
+    seed-42 initialisation the benchmarks use."""
+    g = golden_net
+    torch.manual_seed(42)
+    from othello_reinforcement_learning_test_b200.net import OthelloResNet
+    m = OthelloResNet(5, 64).eval()
+    x = net_oracle.boards_to_tensor(g["self_b"], g["opp_b"])
+    lp, v = net_oracle.forward_bf16_emulated(m.state_dict(), x)
+    assert np.abs(np.exp(lp.numpy()) - np.exp(g["init42_5x64_logp"])).max() < 2e-2
+    assert np.abs(v.numpy().reshape(-1) - g["init42_5x64_value"]).max() < 2e-2
