@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- self-play games/s @50 sims/move, 10x128 ResNet (BASELINE.json metric), on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one self-play campaign: G concurrent games per GPU (default 2368 = 16 x 148 SMs) started
+from the initial position and played to completion with the device-resident engine
+(ParallelSelfPlayWorker / oth_selfplay_run): per ply one search of 1 + 50 leaf evaluations per game
+(select -> tcgen05 ResNet -> expand/backup), move choice, trajectory recording, labelling.
+  value : games finished by all ranks / device time of the K timed steps (weights and buffers resident);
+  e2e   : same campaign through the reference-facing API with HOST buffers: weights re-uploaded from the
+          torch module (the trainer changes them every iteration) and packed trajectories fetched to the
+          host inside the timed region (+ NCCL weight broadcast / trajectory all-gather when N > 1);
+  roofline : bf16 tensor-core roofline of the dominant kernel (k_net_tc), algorithmic FLOPs of the
+          USEFUL leaf evaluations / summed CUDA-event time of its launches inside the timed region;
+  cpu_baseline : the CPU port of the reference's batched self-play (oracle/selfplay_port.py: C tree +
+          fp32 torch network on all host threads) on a bounded sample, N = 1 only.
+`--impl reference` times that CPU port alone (rank 0), same metric / unit / config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "self-play games/s @50 sims/move 10x128 ResNet"
+UNIT = "games/s"
+MEAN_PLIES = 60.5            # measured mean game length of self-play games (reference: 60.2 random, 61 self-play)
+
+
+def flops_per_position(blocks: int, F: int) -> int:
+    """2 x MAC of one forward pass."""
+    return 2 * (64 * 27 * F + blocks * 2 * 64 * 9 * F * F + 64 * 2 * F + 128 * 65 + 64 * F + 64 * 256 + 256)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_sustained": d.get("bf16_tflops_sustained", 1387.2), "bf16_burst": d.get("bf16_tflops", 1660.3),
+                "hbm_gbs": d.get("hbm_gbs", 6555.8), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        busy = [c for c, p in zip(sm, pw) if p > 250.0] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_arm(args, model_sd, budget_s: float, threads=None):
+    from oracle import selfplay_port
+    return selfplay_port.measure_games_per_second(model_sd, num_simulations=args.sims, c_puct=1.0, temperature_threshold=15,
+                                                  num_parallel_games=16, time_budget_s=budget_s, threads=threads,
+                                                  mean_plies_per_game=MEAN_PLIES, seed=1)
+
+
+def build_model(args):
+    import torch
+    from othello_reinforcement_learning_test_b200.net import OthelloResNet
+    torch.manual_seed(42)                           # BASELINE configs: random-init weights, seed 42
+    return OthelloResNet(args.blocks, args.filters).eval()
+
+
+def config_dict(args, world):
+    return {"workload": f"default_8x8 self-play: {args.blocks}x{args.filters} ResNet, {args.sims} sims/move, c_puct 1.0, "
+                        f"temperature threshold 15, Dirichlet noise on; one step = {args.games} concurrent games per GPU "
+                        f"played from the start position to completion",
+            "games_per_step_per_gpu": args.games, "sims_per_move": args.sims, "parallelism": f"games sharded over {world} GPU(s), no "
+            "collective inside the move loop", "weights": "random init, torch.manual_seed(42)",
+            "l2": "256 MiB scratch buffer written between timed steps (L2 flush)", "engine": args.engine}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    model = build_model(args)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    per_step = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        r = cpu_arm(args, model.state_dict(), budget_s=args.cpu_step_seconds, threads=threads)
+        if i >= args.warmup:
+            per_step.append(r)
+        sample = r["sample"]
+    plies = sum(r["plies"] for r in per_step); secs = sum(r["seconds"] for r in per_step)
+    value = plies / secs / MEAN_PLIES
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * secs / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"each step: {sample}"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import othello_reinforcement_learning_test_b200 as pkg
+    from othello_reinforcement_learning_test_b200 import dist as odist
+
+    ctx = pkg.Context.default(local)
+    model = build_model(args)
+    if world > 1:
+        odist.broadcast_weights(model, src=0)
+    worker = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, torch.device("cuda", local), num_simulations=args.sims,
+                                        temperature_threshold=15, num_parallel_games=16, c_puct=1.0, dirichlet_alpha=0.3,
+                                        dirichlet_epsilon=0.25, concurrent_games=args.games, engine=args.engine,
+                                        seed=1000 + rank, verbose=False, ctx=ctx)
+    G = args.games
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def flush_l2():
+        flush.fill_(1)
+        torch.cuda.synchronize()
+
+    net = worker.batch_mcts._native_net()
+    engine = worker._get_engine(G, True)
+
+    def device_step():
+        import ctypes as C
+        ns, ne = C.c_int64(0), C.c_int64(0)
+        pkg._lib.check(ctx.lib.oth_selfplay_run(engine.handle, net.handle, G, C.byref(ns), C.byref(ne)))
+        return int(ns.value), int(ne.value)
+
+    for _ in range(args.warmup):
+        device_step()
+
+    # ---------------- timed: device-resident campaign ----------------
+    sampler = ClockSampler(local)
+    barrier()
+    ctx.timing_enable(True)
+    sampler.start()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    total_ms, samples, evals = 0.0, 0, 0
+    for _ in range(args.steps):
+        flush_l2()
+        ev0.record(stream)
+        ns, ne = device_step()
+        ev1.record(stream)
+        ev1.synchronize()
+        total_ms += ev0.elapsed_time(ev1)
+        samples += ns; evals += ne
+    barrier()
+    wall_s = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    timing = ctx.timing_read()
+    ctx.timing_enable(False)
+    ms = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local}")
+    tot = torch.tensor([float(samples), float(evals), float(launches)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    max_ms = float(ms.item())
+    games_total = G * args.steps * world
+    value = games_total / (max_ms / 1000.0)
+
+    # ---------------- timed: end to end through the public API (host buffers) ----------------
+    h2d = d2h = 0
+    e2e_ms = 0.0
+    barrier()
+    for _ in range(args.steps):
+        flush_l2()
+        ev0.record(stream)
+        if world > 1:
+            h2d += 0 * odist.broadcast_weights(model, src=0)              # NCCL broadcast of the new weights
+        net.sync_from(model, force=True)                                 # fold BN + bf16 pack + H2D
+        smp = worker.execute_episodes_packed(G, add_dirichlet_noise=True)   # campaign + D2H of the packed samples
+        if world > 1:
+            smp = odist.all_gather_samples(smp)                          # trajectories to every rank (replay buffer)
+        ev1.record(stream)
+        ev1.synchronize()
+        e2e_ms += ev0.elapsed_time(ev1)
+        nb, nf = args.blocks, args.filters
+        h2d += (9 * 16 * nf + 2 * nb * 9 * nf * nf) * 2 + (9 * 8 * nf + 2 * nb * 9 * nf * nf) * 4 + 4 * (
+            (1 + 2 * nb) * nf + 3 * nf + 3 + 128 * 65 + 65 + 64 * 256 + 513)
+        d2h += int(worker.last_stats["samples"]) * 168 + 64 * 130
+    barrier()
+    e2 = torch.tensor([e2e_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(e2, op=dist.ReduceOp.MAX)
+    e2e_value = games_total / (float(e2.item()) / 1000.0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- secondary metric: random playouts (BASELINE config 1) ----------------
+    from othello_reinforcement_learning_test_b200 import bitboard as bb
+    n_po = 1 << 24
+    bb.random_playouts(1 << 20, seed=1, ctx=ctx)
+    ev0.record(stream)
+    po = bb.random_playouts(n_po, seed=2, ctx=ctx)
+    ev1.record(stream); ev1.synchronize()
+    po_ms = ev0.elapsed_time(ev1)
+
+    peaks = measured_peaks()
+    fpp = flops_per_position(args.blocks, args.filters)
+    net_ms, net_launches = timing["net"]
+    useful_evals = float(tot[1].item()) / world if world > 1 else float(evals)     # this rank's share for this rank's kernel time
+    useful_evals = float(evals)
+    achieved = useful_evals * fpp / (net_ms / 1000.0) / 1e12 if net_ms > 0 else 0.0
+    launched_positions = net_launches * G
+    roof = {"bound": "tensor", "kernel": "k_net_tc" if args.engine != "simt" else "k_net_simt", "achieved": achieved,
+            "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
+            "traffic": None, "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
+            "flop_per_position": fpp, "useful_positions": int(useful_evals), "launched_positions": int(launched_positions),
+            "kernel_ms_total": net_ms, "kernel_launches": int(net_launches),
+            "kernel_share_of_step": net_ms / total_ms if total_ms else None,
+            "tree_kernels_ms_total": timing["tree"][0], "move_kernels_ms_total": timing["move"][0]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": config_dict(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
+            "gpu_launches": int(tot[2].item()), "clocks": clocks, "roofline": roof,
+            "nn_evals_per_game": float(tot[1].item()) / games_total, "samples_per_game": float(tot[0].item()) / games_total,
+            "wall_s_timed_region": wall_s,
+            "random_playout": {"games_per_s": n_po / (po_ms / 1000.0), "games": n_po,
+                               "mean_plies": po["total_plies"] / n_po, "note": "BASELINE config 1, one game per thread in registers"}}
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_arm(args, model.state_dict(), budget_s=args.cpu_seconds)
+        line["cpu_baseline"] = {"value": r["games_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": r["sample"]}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--games", type=int, default=2368, help="concurrent games per GPU = games per step per GPU")
+    ap.add_argument("--sims", type=int, default=50)
+    ap.add_argument("--blocks", type=int, default=10)
+    ap.add_argument("--filters", type=int, default=128)
+    ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "simt"])
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="time budget of the cpu_baseline sample")
+    ap.add_argument("--cpu-step-seconds", type=float, default=8.0, help="--impl reference: time budget per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        print(f"note: --warmup {args.warmup} < 3 (timing hygiene wants >= 3)", file=sys.stderr)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

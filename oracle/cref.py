@@ -64,6 +64,13 @@ def lib():
     L.ref_policy_from_visits.argtypes = [_i32p, _i32p, C.c_double, _f32p]
     L.ref_mcts_search_hashnet_batch.argtypes = [_u64p, _u64p, C.c_int64, C.c_double, C.c_int, C.c_int,
                                                 _i32p, C.c_void_p]
+    L.ref_batch_create.restype = C.c_void_p
+    L.ref_batch_create.argtypes = [C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
+    L.ref_batch_destroy.argtypes = [C.c_void_p]
+    L.ref_batch_begin.argtypes = [C.c_void_p, _u64p, _u64p, C.c_int]
+    L.ref_batch_collect.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u8p]
+    L.ref_batch_apply.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p]
+    L.ref_batch_visits.argtypes = [C.c_void_p, C.c_int, _i32p, C.c_void_p]
     _lib = L
     return L
 
@@ -229,3 +236,49 @@ def mcts_search_hashnet_batch(s, o, num_simulations: int, c_puct: float = 1.0, t
     if rc != 0:
         raise RuntimeError("ref_mcts_search_hashnet_batch failed")
     return visits, nev
+
+
+class BatchSearch:
+    """Lock-step batch of oracle searches with a batched external evaluator
+    (restates BatchMCTS.search_batch, src/train/parallel_self_play.py:80-197)."""
+
+    def __init__(self, n_games: int, max_simulations: int, c_puct: float = 1.0,
+                 root_n_sum: bool = False, q_canonical: bool = False):
+        self.n_cap = int(n_games)
+        self.h = lib().ref_batch_create(self.n_cap, float(c_puct), int(max_simulations), int(root_n_sum), int(q_canonical))
+        if not self.h:
+            raise MemoryError("ref_batch_create")
+        self.n = 0
+
+    def search(self, s, o, num_simulations: int, evaluate):
+        """evaluate(leaf_self, leaf_opp) -> (probs [k,65] float32, value [k] float32) for the k needed leaves.
+        Returns (visits int32 [n,65], n_evals int32 [n])."""
+        L = lib()
+        s = np.ascontiguousarray(s, np.uint64); o = np.ascontiguousarray(o, np.uint64)
+        n = self.n = int(s.size)
+        if L.ref_batch_begin(self.h, s, o, n) != 0:
+            raise RuntimeError("ref_batch_begin failed")
+        ls = np.empty(n, np.uint64); lo = np.empty(n, np.uint64); need = np.empty(n, np.uint8)
+        probs = np.zeros((n, 65), np.float32); val = np.zeros(n, np.float32)
+        for _ in range(num_simulations + 1):
+            k = L.ref_batch_collect(self.h, n, ls, lo, need)
+            if k:
+                idx = np.flatnonzero(need)
+                p, v = evaluate(ls[idx], lo[idx])
+                probs[idx] = p; val[idx] = np.asarray(v, np.float32).reshape(-1)
+            if L.ref_batch_apply(self.h, n, probs.reshape(-1), val) != 0:
+                raise RuntimeError("ref_batch_apply failed")
+        vis = np.zeros((n, 65), np.int32); nev = np.zeros(n, np.int32)
+        L.ref_batch_visits(self.h, n, vis.reshape(-1), nev.ctypes.data)
+        return vis, nev
+
+    def close(self):
+        if self.h:
+            lib().ref_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -408,63 +408,184 @@ static int pick_child(const tpool *p, int idx, const ref_mcts_cfg *cfg, int pare
     return best_i;
 }
 
+/* One game's search state, steppable: select a leaf -> (evaluate elsewhere) -> apply.  This is
+ * the lock-step shape of BatchMCTS.search_batch (parallel_self_play.py:121-161). */
+typedef struct {
+    tpool pool;
+    int *trail; int trail_cap;
+    uint64_t root_me, root_you;
+    uint64_t leaf_me, leaf_you;
+    int depth, cur, pending, sims_done, n_evals, deepest;
+} gtree;
+
+static int gtree_begin(gtree *g, uint64_t me, uint64_t you, int max_sims)
+{
+    g->pool.len = 0;
+    if (pool_grow(&g->pool, 1)) return -1;
+    tnode *root = &g->pool.v[g->pool.len++];
+    root->value_sum = 0.0; root->prior = 1.0f; root->visit_count = 0;
+    root->first_child = -1; root->n_children = 0; root->action = -1;
+    if (g->trail_cap < max_sims + 8) {
+        free(g->trail);
+        g->trail = (int *)malloc(sizeof(int) * (size_t)(max_sims + 8));
+        g->trail_cap = max_sims + 8;
+    }
+    g->root_me = me; g->root_you = you;
+    g->leaf_me = me; g->leaf_you = you;          /* first request: the root itself (mcts.py:74-75) */
+    g->depth = 0; g->cur = 0; g->pending = 1; g->sims_done = 0; g->n_evals = 0; g->deepest = 0;
+    return 0;
+}
+
+/* mcts.py:100-130: descend; a terminal leaf is scored and backed up at once (pending = 0) */
+static void gtree_select(gtree *g, const ref_mcts_cfg *cfg)
+{
+    uint64_t me = g->root_me, you = g->root_you; int mc = 0;
+    int cur = 0, depth = 0;
+    tpool *pool = &g->pool;
+    while (pool->v[cur].n_children > 0) {                        /* mcts.py:117-123 */
+        int parent_n = pool->v[cur].visit_count;
+        if (cur == 0 && cfg->root_n_sum) parent_n = g->sims_done; /* opt-in: root N = completed sims */
+        int nxt = pick_child(pool, cur, cfg, parent_n);
+        ref_make_move(&me, &you, &mc, 0, pool->v[nxt].action);
+        g->trail[depth++] = nxt;   /* depth <= simulations: every level below the root is an expanded node */
+        cur = nxt;
+    }
+    if (depth > g->deepest) g->deepest = depth;
+    g->depth = depth; g->cur = cur; g->leaf_me = me; g->leaf_you = you;
+    if (ref_is_terminal(me, you)) {                              /* mcts.py:127-130 */
+        double value = (double)ref_winner(me, you);
+        for (int i = depth - 1; i >= 0; --i) {                   /* mcts.py:152-168 */
+            tnode *c = &pool->v[g->trail[i]];
+            c->visit_count += 1; c->value_sum += value; value = -value;
+        }
+        g->sims_done += 1;
+        g->pending = 0;
+    } else {
+        g->pending = 1;
+    }
+}
+
+/* mcts.py:133-148: expand the pending leaf and back its value up */
+static int gtree_apply(gtree *g, const float *probs, float val)
+{
+    if (!g->pending) return 0;
+    if (expand_node(&g->pool, g->cur, probs, g->leaf_me, g->leaf_you)) return -1;
+    g->n_evals += 1;
+    if (g->cur != 0) {
+        double value = (double)val;
+        for (int i = g->depth - 1; i >= 0; --i) {
+            tnode *c = &g->pool.v[g->trail[i]];
+            c->visit_count += 1; c->value_sum += value; value = -value;
+        }
+        g->sims_done += 1;
+    }
+    g->pending = 0;
+    return 0;
+}
+
+static void gtree_root_stats(const gtree *g, int32_t *visits65, double *q65, int *is_child65, int *n_children)
+{
+    const tnode *root = &g->pool.v[0];
+    for (int a = 0; a < 65; ++a) { if (visits65) visits65[a] = 0; if (q65) q65[a] = 0.0; if (is_child65) is_child65[a] = 0; }
+    if (n_children) *n_children = root->n_children;
+    for (int i = 0; i < root->n_children; ++i) {
+        const tnode *c = &g->pool.v[root->first_child + i];
+        if (visits65) visits65[c->action] = c->visit_count;
+        if (q65) q65[c->action] = c->visit_count ? c->value_sum / (double)c->visit_count : 0.0;
+        if (is_child65) is_child65[c->action] = 1;
+    }
+}
+
+static void gtree_free(gtree *g) { free(g->pool.v); free(g->trail); memset(g, 0, sizeof *g); }
+
 int ref_mcts_search(uint64_t self_b, uint64_t opp_b, const ref_mcts_cfg *cfg,
                     ref_eval_fn eval, void *user, ref_mcts_result *out)
 {
-    tpool pool = {0, 0, 0};
-    if (pool_grow(&pool, 1)) return -1;
-    tnode *root = &pool.v[pool.len++];
-    root->value_sum = 0.0; root->prior = 1.0f; root->visit_count = 0;
-    root->first_child = -1; root->n_children = 0; root->action = -1;
-
+    gtree g; memset(&g, 0, sizeof g);
     float probs[65], val;
-    int n_evals = 0, deepest = 0;
-    eval(self_b, opp_b, probs, &val, user); ++n_evals;           /* mcts.py:74-75 */
-    if (expand_node(&pool, 0, probs, self_b, opp_b)) { free(pool.v); return -1; }
-
-    int *trail = (int *)malloc(sizeof(int) * (size_t)(cfg->num_simulations + 8));
+    if (gtree_begin(&g, self_b, opp_b, cfg->num_simulations)) return -1;
+    eval(self_b, opp_b, probs, &val, user);                      /* mcts.py:74-75 */
+    if (gtree_apply(&g, probs, val)) { gtree_free(&g); return -1; }
     for (int s = 0; s < cfg->num_simulations; ++s) {             /* mcts.py:89-92 */
-        uint64_t me = self_b, you = opp_b; int mc = 0;
-        int cur = 0, depth = 0;
-        while (pool.v[cur].n_children > 0) {                     /* mcts.py:117-123 */
-            int parent_n = pool.v[cur].visit_count;
-            if (cur == 0 && cfg->root_n_sum) parent_n = s;       /* opt-in: root N = completed sims */
-            int nxt = pick_child(&pool, cur, cfg, parent_n);
-            ref_make_move(&me, &you, &mc, 0, pool.v[nxt].action);
-            trail[depth++] = nxt;   /* depth <= simulations: every level below the root is an expanded node */
-            cur = nxt;
-        }
-        if (depth > deepest) deepest = depth;
-        double value;
-        if (ref_is_terminal(me, you)) {                          /* mcts.py:127-130 */
-            value = (double)ref_winner(me, you);
-        } else {                                                 /* mcts.py:133-144 */
-            eval(me, you, probs, &val, user); ++n_evals;
-            if (expand_node(&pool, cur, probs, me, you)) { free(trail); free(pool.v); return -1; }
-            value = (double)val;
-        }
-        for (int i = depth - 1; i >= 0; --i) {                   /* mcts.py:152-168 */
-            tnode *c = &pool.v[trail[i]];
-            c->visit_count += 1;
-            c->value_sum += value;
-            value = -value;
+        gtree_select(&g, cfg);
+        if (g.pending) {
+            eval(g.leaf_me, g.leaf_you, probs, &val, user);
+            if (gtree_apply(&g, probs, val)) { gtree_free(&g); return -1; }
         }
     }
-
     memset(out, 0, sizeof *out);
-    root = &pool.v[0];
-    out->n_children = root->n_children;
-    for (int i = 0; i < root->n_children; ++i) {
-        const tnode *c = &pool.v[root->first_child + i];
-        out->visits[c->action] = c->visit_count;
-        out->q[c->action] = c->visit_count ? c->value_sum / (double)c->visit_count : 0.0;
-        out->is_child[c->action] = 1;
-    }
-    out->n_evals = n_evals;
-    out->max_depth = deepest;
-    free(trail);
-    free(pool.v);
+    gtree_root_stats(&g, out->visits, out->q, out->is_child, &out->n_children);
+    out->n_evals = g.n_evals;
+    out->max_depth = g.deepest;
+    gtree_free(&g);
     return 0;
+}
+
+/* ---- lock-step batch of searches with an external (batched) evaluator ---------------------- */
+struct ref_batch {
+    int n; ref_mcts_cfg cfg; gtree *g; int root_phase;
+};
+
+ref_batch *ref_batch_create(int n_games, double c_puct, int max_simulations, int root_n_sum, int q_canonical)
+{
+    ref_batch *b = (ref_batch *)calloc(1, sizeof *b);
+    if (!b) return 0;
+    b->n = n_games;
+    b->cfg.c_puct = c_puct; b->cfg.num_simulations = max_simulations;
+    b->cfg.root_n_sum = root_n_sum; b->cfg.q_canonical = q_canonical;
+    b->g = (gtree *)calloc((size_t)n_games, sizeof(gtree));
+    return b;
+}
+
+void ref_batch_destroy(ref_batch *b)
+{
+    if (!b) return;
+    for (int i = 0; i < b->n; ++i) gtree_free(&b->g[i]);
+    free(b->g); free(b);
+}
+
+int ref_batch_begin(ref_batch *b, const uint64_t *self_b, const uint64_t *opp_b, int n)
+{
+    if (n > b->n) return -1;
+    for (int i = 0; i < n; ++i)
+        if (gtree_begin(&b->g[i], self_b[i], opp_b[i], b->cfg.num_simulations)) return -1;
+    for (int i = n; i < b->n; ++i) b->g[i].pending = 0;
+    b->root_phase = 1;
+    return 0;
+}
+
+/* one lock-step: every game selects a leaf (first call after begin: the roots).  Returns the
+ * number of leaves that need the evaluator. */
+int ref_batch_collect(ref_batch *b, int n, uint64_t *leaf_self, uint64_t *leaf_opp, uint8_t *need)
+{
+    int cnt = 0;
+    if (!b->root_phase) {
+#pragma omp parallel for schedule(static) if (n >= 64)
+        for (int i = 0; i < n; ++i) gtree_select(&b->g[i], &b->cfg);
+    }
+    b->root_phase = 0;
+    for (int i = 0; i < n; ++i) {
+        leaf_self[i] = b->g[i].leaf_me; leaf_opp[i] = b->g[i].leaf_you;
+        need[i] = (uint8_t)b->g[i].pending;
+        cnt += b->g[i].pending;
+    }
+    return cnt;
+}
+
+int ref_batch_apply(ref_batch *b, int n, const float *probs, const float *value)
+{
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad) if (n >= 64)
+    for (int i = 0; i < n; ++i) bad |= gtree_apply(&b->g[i], probs + (size_t)i * 65, value[i]) ? 1 : 0;
+    return bad ? -1 : 0;
+}
+
+void ref_batch_visits(const ref_batch *b, int n, int32_t *visits, int32_t *n_evals)
+{
+    for (int i = 0; i < n; ++i) {
+        gtree_root_stats(&b->g[i], visits + (size_t)i * 65, 0, 0, 0);
+        if (n_evals) n_evals[i] = b->g[i].n_evals;
+    }
 }
 
 int ref_mcts_search_hashnet_batch(const uint64_t *self_b, const uint64_t *opp_b, int64_t n,

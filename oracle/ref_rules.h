@@ -95,6 +95,17 @@ typedef struct {
 int ref_mcts_search(uint64_t self_b, uint64_t opp_b, const ref_mcts_cfg *cfg,
                     ref_eval_fn eval, void *user, ref_mcts_result *out);
 
+/* lock-step batch of searches with an external, batched evaluator: the shape of
+ * BatchMCTS.search_batch (src/train/parallel_self_play.py:80-197).  collect -> evaluate the
+ * leaves with need[i] != 0 -> apply; the first collect after begin returns the roots. */
+typedef struct ref_batch ref_batch;
+ref_batch *ref_batch_create(int n_games, double c_puct, int max_simulations, int root_n_sum, int q_canonical);
+void ref_batch_destroy(ref_batch *b);
+int ref_batch_begin(ref_batch *b, const uint64_t *self_b, const uint64_t *opp_b, int n);
+int ref_batch_collect(ref_batch *b, int n, uint64_t *leaf_self, uint64_t *leaf_opp, uint8_t *need);
+int ref_batch_apply(ref_batch *b, int n, const float *probs, const float *value);
+void ref_batch_visits(const ref_batch *b, int n, int32_t *visits, int32_t *n_evals);
+
 /* masked renormalisation used by MCTSNode.expand (node.py:62-89) in numpy's
  * float32 arithmetic (pairwise 8-lane summation order); priors[65] out. */
 void ref_expand_priors(const float *probs65, const int *legal, int n_legal, float *priors65);

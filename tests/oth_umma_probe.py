@@ -3,7 +3,10 @@ Executed in a subprocess by tests/test_gpu_e_umma_probe.py (and by tools/gpu_fir
 faulting kernel cannot take the test process down with it."""
 import ctypes as C
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 
