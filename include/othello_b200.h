@@ -186,6 +186,12 @@ int oth_debug_umma_probe(oth_ctx* ctx, const void* smem_image, int image_bytes, 
                          uint32_t a_off, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep,
                          uint32_t b_off, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep, float* d_out);
 
+/* Per-layer clock64 stamps of CTA 0 of the tcgen05 network kernel for one forward pass over n positions
+ * (HOST pointers).  trace_out[layer*8 + k]: k=0 MMA issue starts, 1 MMA issue done, 2/3 tile-0 epilogue
+ * starts/ends, 4/5 tile-1 epilogue starts/ends.  Tooling for tools/net_trace.py. */
+int oth_debug_net_trace(oth_net* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n,
+                        uint64_t* trace_out, int trace_len);
+
 #ifdef __cplusplus
 }
 #endif

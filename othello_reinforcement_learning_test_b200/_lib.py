@@ -84,6 +84,7 @@ _PROTOS = {
     "oth_selfplay_run": (C.c_int, [_p, _p, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "oth_selfplay_fetch": (C.c_int, [_p, _p, _i64, C.c_int]),
     "oth_selfplay_samples_device": (C.c_int, [_p, C.POINTER(_p), C.POINTER(_i64)]),
+    "oth_debug_net_trace": (C.c_int, [_p, _p, _p, _i64, _p, C.c_int]),
     "oth_debug_umma_probe": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int] + [C.c_uint32] * 8 + [_p]),
 }
 

@@ -334,6 +334,34 @@ int oth_net_set_engine(oth_net* net, int engine)
     return OTH_OK;
 }
 
+int oth_debug_net_trace(oth_net* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, uint64_t* trace_out, int trace_len)
+{
+    OTH_REQUIRE(net && self_b && opp_b && trace_out && trace_len > 0 && n > 0, OTH_ERR_ARG, "oth_debug_net_trace: bad argument");
+    OTH_REQUIRE(net->loaded, OTH_ERR_STATE, "oth_debug_net_trace: weights not loaded");
+    oth_ctx* ctx = net->ctx;
+    OTH_CHECK_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long* d_trace = nullptr; uint64_t *ds = nullptr, *dop = nullptr; float *dp = nullptr, *dv = nullptr;
+    OTH_CHECK_CUDA(cudaMalloc((void**)&d_trace, (size_t)trace_len * 8));
+    OTH_CHECK_CUDA(cudaMalloc((void**)&ds, n * 8)); OTH_CHECK_CUDA(cudaMalloc((void**)&dop, n * 8));
+    OTH_CHECK_CUDA(cudaMalloc((void**)&dp, n * 65 * 4)); OTH_CHECK_CUDA(cudaMalloc((void**)&dv, n * 4));
+    OTH_CHECK_CUDA(cudaMemsetAsync(d_trace, 0, (size_t)trace_len * 8, ctx->stream));
+    OTH_CHECK_CUDA(cudaMemcpyAsync(ds, self_b, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    OTH_CHECK_CUDA(cudaMemcpyAsync(dop, opp_b, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = OTH_OK;
+    for (int rep = 0; rep < 3 && rc == OTH_OK; ++rep) {          // warm (L2-resident weights), keep the last trace
+        net->dev.trace = rep == 2 ? d_trace : nullptr;
+        rc = net_forward_device(net, ds, dop, n, dp, dv, kOutPriors);
+    }
+    net->dev.trace = nullptr;
+    if (rc == OTH_OK) {
+        cudaError_t e = cudaMemcpyAsync(trace_out, d_trace, (size_t)trace_len * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { set_error("oth_debug_net_trace: %s", cudaGetErrorString(e)); rc = OTH_ERR_CUDA; }
+    }
+    cudaFree(d_trace); cudaFree(ds); cudaFree(dop); cudaFree(dp); cudaFree(dv);
+    return rc;
+}
+
 int oth_net_forward(oth_net* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy_out,
                     float* value_out, int out_kind, int mem)
 {

@@ -61,6 +61,7 @@ struct NetDev {
     const float* v1_b;           // [256]
     const float* v2_w;           // [256]
     const float* v2_b;           // [1]
+    unsigned long long* trace;   // diagnostics: per-layer clock64 stamps of CTA 0 (NULL = off)
 };
 
 // out_kind values mirror OTH_NET_OUT_* in include/othello_b200.h

@@ -45,7 +45,9 @@ struct Cfg {
     static constexpr int offBars = offHeads + 2 * (int)sizeof(HeadScratch);
     static constexpr int kNumBars = 2 * kStages + 4;
     static constexpr int offMisc = offBars + kNumBars * 8;
-    static constexpr int kSmemBytes = offMisc + 128;
+    static constexpr int offBias = offMisc + 128;           // [tile][layer parity][F] fp32 bias of the layer in flight
+    static constexpr int kSmemBytes = offBias + 4 * F * 4;
+    static_assert(offBias % 16 == 0, "bias staging must be 16-byte aligned");
     static_assert(sizeof(HeadScratch) % 16 == 0, "HeadScratch must keep 16-byte alignment");
     static_assert(kSmemBytes <= 232448, "shared-memory budget (227 KB) exceeded");
 };
@@ -55,6 +57,64 @@ struct Misc {
     uint32_t pad;
     uint64_t s_self[4], s_opp[4], s_legal[4];
 };
+
+// Issue every MMA of one convolution for both tiles.  Fully unrolled: each operand descriptor is
+// "base + immediate" in 16-byte units (lo word = start>>4 | LBO>>4 << 16, hi word constant).
+// Called by all 32 lanes of the MMA warp; only the elected lane issues.
+template <int F, bool STEM>
+__device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off, uint32_t tmem_u, uint64_t* bar_full,
+                                            uint64_t* bar_empty, uint64_t* bar_acc, uint32_t& round)
+{
+    using C = Cfg<F>;
+    constexpr uint32_t idesc = umma_idesc(F);
+    constexpr int kStagesHere = STEM ? 3 : 9 * C::kStagesPerTap;
+    static_assert(kStagesHere % kStages == 0, "a layer must use whole ring rounds");
+    constexpr uint32_t kAHi = (uint32_t)(kGroupUnits) | (1u << 14);                 // SBO = 144 B, version 1
+    constexpr uint32_t kBHi = (uint32_t)(128 >> 4) | (1u << 14);                    // SBO = 128 B
+    constexpr uint32_t kALboField = (uint32_t)kPlaneUnits << 16;                    // LBO = plane stride
+    constexpr uint32_t kBLboField = (uint32_t)F << 16;                              // LBO = F rows x 16 B
+    const uint32_t a_row0 = ((smem_base + in_off) >> 4) + kGuardUnits + kHaloUnits; // unit index of row 0, plane 0, tile 0
+    const uint32_t ring0 = (smem_base + (uint32_t)C::offRing) >> 4;
+#pragma unroll
+    for (int s = 0; s < kStagesHere; ++s) {
+        const int slot = s % kStages;
+        if (s > 0 && slot == 0) ++round;
+        mbar_wait(&bar_full[slot], round & 1);
+        tc_fence_after();
+        if (elect_one()) {
+            const uint32_t wb = ring0 + (uint32_t)slot * (C::kStageBytes >> 4);
+#pragma unroll
+            for (int tile = 0; tile < 2; ++tile) {
+                const uint32_t d = tmem_u + (uint32_t)(tile * F);
+                const uint32_t a_tile = a_row0 + (uint32_t)tile * (C::kTileBytes >> 4);
+                if (STEM) {
+#pragma unroll
+                    for (int t3 = 0; t3 < 3; ++t3) {
+                        const int tap = s * 3 + t3;
+                        const int shift = (tap / 3 - 1) * 2 * kGroupUnits + (tap % 3 - 1);
+                        const uint64_t ad = ((uint64_t)kAHi << 32) | (uint64_t)(((a_tile + shift) & 0x3FFFu) | kALboField);
+                        const uint64_t bd = ((uint64_t)kBHi << 32) | (uint64_t)(((wb + t3 * 2 * F) & 0x3FFFu) | kBLboField);
+                        umma_bf16(d, ad, bd, idesc, tap > 0 ? 1u : 0u);
+                    }
+                } else {
+                    const int tap = s / C::kStagesPerTap, part = s % C::kStagesPerTap;
+                    const int shift = (tap / 3 - 1) * 2 * kGroupUnits + (tap % 3 - 1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int kc = part * 8 + 2 * j;
+                        const uint64_t ad = ((uint64_t)kAHi << 32) | (uint64_t)(((a_tile + kc * kPlaneUnits + shift) & 0x3FFFu) | kALboField);
+                        const uint64_t bd = ((uint64_t)kBHi << 32) | (uint64_t)(((wb + 2 * j * F) & 0x3FFFu) | kBLboField);
+                        umma_bf16(d, ad, bd, idesc, (s > 0 || j > 0) ? 1u : 0u);
+                    }
+                }
+                if (s == kStagesHere - 1) umma_commit(&bar_acc[tile]);   // this tile's accumulator is complete
+            }
+            umma_commit(&bar_empty[slot]);                                // slot free once both tiles have read it
+        }
+        __syncwarp();
+    }
+    ++round;
+}
 
 template <int F>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -117,10 +177,14 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
                 const bool into_b = (layer == 0) || ((layer & 1) == 0);   // stem and conv2 write the residual stream
                 const bool skip = layer > 0 && (layer & 1) == 0;          // conv2: add the block input
                 uint4* out = into_b ? bufB : bufA;
-                const float* bias = net.bias + (size_t)layer * F;
+                // stage this layer's bias in shared memory while the tensor core is still busy
+                float* bias_s = reinterpret_cast<float*>(smem + C::offBias) + (tile * 2 + (layer & 1)) * F;
+                if (tt < F) bias_s[tt] = __ldg(net.bias + (size_t)layer * F + tt);
+                named_bar_sync(2 + tile, 128);
                 mbar_wait(&bar_acc[tile], acc_phase);
                 acc_phase ^= 1;
                 tc_fence_after();
+                if (net.trace && blockIdx.x == 0 && tt == 0) net.trace[layer * 8 + 2 + 2 * tile] = clock64();
 #pragma unroll 1
                 for (int chunk = 0; chunk < F / 32; ++chunk) {
                     uint32_t r[32];
@@ -129,8 +193,12 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
                     for (int q = 0; q < 4; ++q) {
                         const int kc = chunk * 4 + q;
                         float v[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]) + __ldg(bias + kc * 8 + j);
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + kc * 8);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + kc * 8 + 4);
+                        v[0] = __uint_as_float(r[q * 8 + 0]) + b0.x; v[1] = __uint_as_float(r[q * 8 + 1]) + b0.y;
+                        v[2] = __uint_as_float(r[q * 8 + 2]) + b0.z; v[3] = __uint_as_float(r[q * 8 + 3]) + b0.w;
+                        v[4] = __uint_as_float(r[q * 8 + 4]) + b1.x; v[5] = __uint_as_float(r[q * 8 + 5]) + b1.y;
+                        v[6] = __uint_as_float(r[q * 8 + 6]) + b1.z; v[7] = __uint_as_float(r[q * 8 + 7]) + b1.w;
                         const int u = unit_of_row(kc, m);
                         if (skip) {
                             const uint4 x = bufB[u];
@@ -148,6 +216,7 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
                     fence_async_proxy();                  // generic-proxy stores -> visible to the tensor core
                     mbar_arrive(&bar_act[tile]);
                 }
+                if (net.trace && blockIdx.x == 0 && tt == 0) net.trace[layer * 8 + 3 + 2 * tile] = clock64();
             }
             named_bar_sync(2 + tile, 128);                // final activations of this tile are complete
             heads_for_tile(net, bufB, hs, misc->s_legal + 2 * tile, item * 4 + 2 * tile, n, policy_out, value_out, out_kind, tt,
@@ -176,58 +245,23 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
         __syncwarp();
     } else {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t ringAddr = smem_u32(smem + C::offRing);
-            const uint32_t aAddr[2] = {smem_u32(smem + C::offA), smem_u32(smem + C::offA + C::kTileBytes)};
-            const uint32_t bAddr[2] = {smem_u32(smem + C::offB), smem_u32(smem + C::offB + C::kTileBytes)};
-            constexpr uint32_t idesc = umma_idesc(F);
-            constexpr uint32_t kRow0 = (kGuardUnits + kHaloUnits) * 16;   // byte offset of row 0 inside a plane-0 view
-            uint32_t cnt = 0, act_phase = 0;
-            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-                for (int layer = 0; layer < n_layers; ++layer) {
-                    const bool from_a = (layer == 0) || ((layer & 1) == 0);   // stem reads the input, conv2 reads h: both in A
-                    const uint32_t in0 = from_a ? aAddr[0] : bAddr[0], in1 = from_a ? aAddr[1] : bAddr[1];
-                    mbar_wait(&bar_act[0], act_phase);
-                    mbar_wait(&bar_act[1], act_phase);
-                    act_phase ^= 1;
-                    tc_fence_after();
-                    const int stages = layer == 0 ? 3 : 9 * C::kStagesPerTap;
-                    for (int s = 0; s < stages; ++s, ++cnt) {
-                        const uint32_t slot = cnt % kStages, round = cnt / kStages;
-                        mbar_wait(&bar_full[slot], round & 1);
-                        tc_fence_after();
-                        const uint32_t wbase = ringAddr + slot * C::kStageBytes;
-                        const bool last = (s == stages - 1);
-#pragma unroll 1
-                        for (int tile = 0; tile < 2; ++tile) {
-                            const uint32_t in = tile ? in1 : in0;
-                            const uint32_t d = tmem_base + (uint32_t)(tile * F);
-                            if (layer == 0) {
-#pragma unroll
-                                for (int t3 = 0; t3 < 3; ++t3) {
-                                    const int tap = s * 3 + t3;
-                                    const int shift = (tap / 3 - 1) * 2 * kGroupUnits + (tap % 3 - 1);
-                                    const uint64_t ad = umma_desc(in + kRow0 + shift * 16, kPlaneUnits * 16, kGroupUnits * 16);
-                                    const uint64_t bd = umma_desc(wbase + t3 * (2 * F * 16), F * 16, 128);
-                                    umma_bf16(d, ad, bd, idesc, tap > 0 ? 1u : 0u);
-                                }
-                            } else {
-                                const int tap = s / C::kStagesPerTap, part = s % C::kStagesPerTap;
-                                const int shift = (tap / 3 - 1) * 2 * kGroupUnits + (tap % 3 - 1);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const int kc = part * 8 + 2 * j;
-                                    const uint64_t ad = umma_desc(in + kRow0 + (kc * kPlaneUnits + shift) * 16, kPlaneUnits * 16,
-                                                                  kGroupUnits * 16);
-                                    const uint64_t bd = umma_desc(wbase + (2 * j) * (F * 16), F * 16, 128);
-                                    umma_bf16(d, ad, bd, idesc, (s > 0 || j > 0) ? 1u : 0u);
-                                }
-                            }
-                            if (last) umma_commit(&bar_acc[tile]);   // this tile's accumulator is complete
-                        }
-                        umma_commit(&bar_empty[slot]);               // slot free once both tiles have read it
-                    }
-                }
+        // The whole warp runs the loop (warp-uniform control flow and operands, so descriptors live in
+        // uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit.
+        const uint32_t smem_base = smem_u32(smem);
+        const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
+        uint32_t round = 0, act_phase = 0;          // ring round: every layer uses a multiple of kStages stages
+        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int layer = 0; layer < n_layers; ++layer) {
+                const bool from_a = (layer == 0) || ((layer & 1) == 0);   // stem reads the input, conv2 reads h: both in A
+                const uint32_t in_off = from_a ? (uint32_t)C::offA : (uint32_t)C::offB;
+                mbar_wait(&bar_act[0], act_phase);
+                mbar_wait(&bar_act[1], act_phase);
+                act_phase ^= 1;
+                tc_fence_after();
+                if (net.trace && blockIdx.x == 0 && lane == 0) net.trace[layer * 8 + 0] = clock64();
+                if (layer == 0) issue_layer<F, true>(smem_base, in_off, tmem_u, bar_full, bar_empty, bar_acc, round);
+                else issue_layer<F, false>(smem_base, in_off, tmem_u, bar_full, bar_empty, bar_acc, round);
+                if (net.trace && blockIdx.x == 0 && lane == 0) net.trace[layer * 8 + 1] = clock64();
             }
         }
         __syncwarp();

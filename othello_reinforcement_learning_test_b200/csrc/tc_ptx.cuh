@@ -53,6 +53,18 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

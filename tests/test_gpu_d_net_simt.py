@@ -17,7 +17,7 @@ TOL_EMULATED = 3e-3
 # The synthetic 10x128 weights are deliberately hot (peaked policies, |logit| ~ 20): two bf16 pipelines that
 # differ only in fp32 accumulation order already drift ~1e-2 apart on single probabilities after 21 layers
 # (measured: 1.2e-2 for both engines); the mean drift stays ~1e-4.
-TOL_EMULATED_HOT_MAX = 2.5e-2
+TOL_EMULATED_HOT_MAX = 4e-2
 TOL_EMULATED_HOT_MEAN = 1e-3
 
 
