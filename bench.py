@@ -117,7 +117,8 @@ def config_dict(args, world):
                         f"played from the start position to completion",
             "games_per_step_per_gpu": args.games, "sims_per_move": args.sims, "parallelism": f"games sharded over {world} GPU(s), no "
             "collective inside the move loop", "weights": "random init, torch.manual_seed(42)",
-            "l2": "256 MiB scratch buffer written between timed steps (L2 flush)", "engine": args.engine}
+            "l2": "256 MiB scratch buffer written between timed steps (L2 flush)", "engine": args.engine,
+            "eval_cache": not args.no_eval_cache}
 
 
 def run_reference(args):
@@ -167,7 +168,7 @@ def run_b200(args):
     worker = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, torch.device("cuda", local), num_simulations=args.sims,
                                         temperature_threshold=15, num_parallel_games=16, c_puct=1.0, dirichlet_alpha=0.3,
                                         dirichlet_epsilon=0.25, concurrent_games=args.games, engine=args.engine,
-                                        seed=1000 + rank, verbose=False, ctx=ctx)
+                                        seed=1000 + rank, verbose=False, eval_cache=not args.no_eval_cache, ctx=ctx)
     G = args.games
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
@@ -184,14 +185,20 @@ def run_b200(args):
     net = worker.batch_mcts._native_net()
     engine = worker._get_engine(G, True)
 
+    cache_stats = np.zeros(4, np.int64)
+
     def device_step():
         import ctypes as C
         ns, ne = C.c_int64(0), C.c_int64(0)
         pkg._lib.check(ctx.lib.oth_selfplay_run(engine.handle, net.handle, G, C.byref(ns), C.byref(ne)))
+        st = (C.c_uint64 * 4)()
+        pkg._lib.check(ctx.lib.oth_selfplay_stats(engine.handle, st))
+        cache_stats[:] += np.array(list(st), np.int64)
         return int(ns.value), int(ne.value)
 
     for _ in range(args.warmup):
         device_step()
+    cache_stats[:] = 0
 
     # ---------------- timed: device-resident campaign ----------------
     sampler = ClockSampler(local)
@@ -268,10 +275,9 @@ def run_b200(args):
     peaks = measured_peaks()
     fpp = flops_per_position(args.blocks, args.filters)
     net_ms, net_launches = timing["net"]
-    useful_evals = float(tot[1].item()) / world if world > 1 else float(evals)     # this rank's share for this rank's kernel time
-    useful_evals = float(evals)
+    useful_evals = float(cache_stats[0])       # positions the network really evaluated on this rank (compacted, de-duplicated)
     achieved = useful_evals * fpp / (net_ms / 1000.0) / 1e12 if net_ms > 0 else 0.0
-    launched_positions = net_launches * G
+    launched_positions = useful_evals
     roof = {"bound": "tensor", "kernel": "k_net_tc" if args.engine != "simt" else "k_net_simt", "achieved": achieved,
             "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
             "traffic": None, "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
@@ -285,7 +291,11 @@ def run_b200(args):
             "dtype": "bf16", "data": "synthetic", "config": config_dict(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
             "gpu_launches": int(tot[2].item()), "clocks": clocks, "roofline": roof,
-            "nn_evals_per_game": float(tot[1].item()) / games_total, "samples_per_game": float(tot[0].item()) / games_total,
+            "expansions_per_game": float(tot[1].item()) / games_total, "samples_per_game": float(tot[0].item()) / games_total,
+            "eval_cache": {"enabled": not args.no_eval_cache, "rank0_expansions": int(evals), "rank0_network_positions": int(cache_stats[0]),
+                           "rank0_cache_hits": int(cache_stats[1]), "rank0_same_step_duplicates": int(cache_stats[2]),
+                           "rank0_hash_collisions": int(cache_stats[3]),
+                           "note": "result-transparent: cached / shared outputs are bit-identical to re-evaluation; cache is emptied at the start of every campaign"},
             "wall_s_timed_region": wall_s,
             "random_playout": {"games_per_s": n_po / (po_ms / 1000.0), "games": n_po,
                                "mean_plies": po["total_plies"] / n_po, "note": "BASELINE config 1, one game per thread in registers"}}
@@ -314,6 +324,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="time budget of the cpu_baseline sample")
     ap.add_argument("--cpu-step-seconds", type=float, default=8.0, help="--impl reference: time budget per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval-cache", action="store_true", help="evaluate every leaf with the network (no position cache / dedup)")
     args = ap.parse_args()
     if args.warmup < 3:
         print(f"note: --warmup {args.warmup} < 3 (timing hygiene wants >= 3)", file=sys.stderr)

@@ -119,6 +119,8 @@ int oth_net_forward(oth_net* net, const uint64_t* self_b, const uint64_t* opp_b,
 #define OTH_FLAG_Q_CANONICAL 2u  /* negate child Q in select; default: un-negated (node.py:113,119) */
 #define OTH_FLAG_WINNER_BLACK 4u /* self-play labels from black's view; default: parallel_self_play.py:397-404 */
 #define OTH_FLAG_EVAL_HASHNET 8u /* built-in integer test evaluator instead of the network */
+#define OTH_FLAG_EVAL_CACHE 16u  /* position-keyed evaluation cache + same-step dedup in HBM (result-transparent:
+                                    the network's output for a position does not depend on its batch slot) */
 
 int oth_search_create(oth_ctx* ctx, int64_t max_games, int max_simulations, oth_search** out);
 int oth_search_destroy(oth_search* s);
@@ -139,6 +141,11 @@ int oth_search_run(oth_search* s, oth_net* net, int num_simulations, int add_dir
 /* root child statistics: visits int32 [n,65], q float64 [n,65] (0 for non-children),
  * n_evals int32 [n].  Any may be NULL. */
 int oth_search_results(oth_search* s, int32_t* visits, double* q, int32_t* n_evals, int mem);
+/* evaluation statistics since the last call (HOST uint64[4]): network positions actually evaluated, cache hits,
+ * same-step duplicates, hash collisions.  n_evals in oth_search_results keeps counting expansions, like the reference. */
+int oth_search_stats(oth_search* s, uint64_t* out4);
+/* forget every cached evaluation (call when the network's weights changed) */
+int oth_search_invalidate_cache(oth_search* s);
 /* get_policy_distribution (node.py:147-182): float32 [n,65] for temperature 0 or 1 (others: powf) */
 int oth_search_policy(oth_search* s, double temperature, float* policy_out, int mem);
 
@@ -172,6 +179,8 @@ int oth_selfplay_destroy(oth_selfplay* sp);
  * n_samples_out / n_evals_out are HOST scalars. */
 int oth_selfplay_run(oth_selfplay* sp, oth_net* net, int64_t num_episodes, int64_t* n_samples_out,
                      int64_t* n_evals_out);
+/* evaluation statistics of the last run (HOST uint64[4]), as oth_search_stats */
+int oth_selfplay_stats(oth_selfplay* sp, uint64_t* out4);
 /* copy the samples of the last run into a caller buffer (HOST or DEVICE) */
 int oth_selfplay_fetch(oth_selfplay* sp, oth_sample* out, int64_t capacity, int mem);
 /* device pointer + count of the last run's samples (for NCCL all-gather without a host hop) */

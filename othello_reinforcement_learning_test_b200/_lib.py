@@ -19,7 +19,7 @@ OTH_OK = 0
 MEM_DEVICE, MEM_HOST = 0, 1
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
 OUT_LOGPROBS, OUT_PROBS, OUT_PRIORS = 0, 1, 2
-FLAG_ROOT_N_SUM, FLAG_Q_CANONICAL, FLAG_WINNER_BLACK, FLAG_EVAL_HASHNET = 1, 2, 4, 8
+FLAG_ROOT_N_SUM, FLAG_Q_CANONICAL, FLAG_WINNER_BLACK, FLAG_EVAL_HASHNET, FLAG_EVAL_CACHE = 1, 2, 4, 8, 16
 ACTIONS = 65
 
 
@@ -79,6 +79,9 @@ _PROTOS = {
     "oth_search_run": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_uint64]),
     "oth_search_results": (C.c_int, [_p, _p, _p, _p, C.c_int]),
     "oth_search_policy": (C.c_int, [_p, C.c_double, _p, C.c_int]),
+    "oth_search_stats": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
+    "oth_search_invalidate_cache": (C.c_int, [_p]),
+    "oth_selfplay_stats": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
     "oth_selfplay_create": (C.c_int, [_p, C.POINTER(SelfPlayConfig), C.POINTER(_p)]),
     "oth_selfplay_destroy": (C.c_int, [_p]),
     "oth_selfplay_run": (C.c_int, [_p, _p, _i64, C.POINTER(_i64), C.POINTER(_i64)]),

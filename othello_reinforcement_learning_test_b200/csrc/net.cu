@@ -219,8 +219,9 @@ template <int CPT>
 __global__ void __launch_bounds__(kSimtThreads) k_net_simt(NetDev net, const uint64_t* __restrict__ self_b,
                                                            const uint64_t* __restrict__ opp_b, int64_t n,
                                                            float* __restrict__ policy_out, float* __restrict__ value_out,
-                                                           int out_kind)
+                                                           int out_kind, const int32_t* __restrict__ n_dev)
 {
+    if (n_dev) { const int64_t nd = *n_dev; n = nd < n ? nd : n; }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int KC = net.KC, F = net.F;
     const int bytes = tile_buffer_bytes(KC);
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(kSimtThreads) k_net_simt(NetDev net, const uin
 }
 
 int net_forward_simt(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value,
-                     int out_kind)
+                     int out_kind, const int32_t* n_dev)
 {
     oth_ctx* ctx = net->ctx;
     const int F = net->F;
@@ -273,7 +274,7 @@ int net_forward_simt(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b
 #define OTH_SIMT_CASE(cpt)                                                                                          \
     case cpt: {                                                                                                     \
         OTH_CHECK_CUDA(cudaFuncSetAttribute(k_net_simt<cpt>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   \
-        k_net_simt<cpt><<<grid, kSimtThreads, smem, ctx->stream>>>(net->dev, self_b, opp_b, n, policy, value, out_kind); \
+        k_net_simt<cpt><<<grid, kSimtThreads, smem, ctx->stream>>>(net->dev, self_b, opp_b, n, policy, value, out_kind, n_dev); \
     } break;
     switch (F / 2) {
         OTH_SIMT_CASE(8) OTH_SIMT_CASE(16) OTH_SIMT_CASE(24) OTH_SIMT_CASE(32) OTH_SIMT_CASE(40) OTH_SIMT_CASE(48)
@@ -384,10 +385,10 @@ int oth_net_forward(oth_net* net, const uint64_t* self_b, const uint64_t* opp_b,
 
 namespace oth {
 int net_forward_device(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value,
-                       int out_kind)
+                       int out_kind, const int32_t* n_dev)
 {
     TimedLaunch timed(net->ctx, 0);
-    if (net->engine == OTH_NET_ENGINE_TCGEN05) return net_forward_tc(net, self_b, opp_b, n, policy, value, out_kind);
-    return net_forward_simt(net, self_b, opp_b, n, policy, value, out_kind);
+    if (net->engine == OTH_NET_ENGINE_TCGEN05) return net_forward_tc(net, self_b, opp_b, n, policy, value, out_kind, n_dev);
+    return net_forward_simt(net, self_b, opp_b, n, policy, value, out_kind, n_dev);
 }
 }  // namespace oth

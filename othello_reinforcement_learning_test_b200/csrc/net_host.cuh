@@ -26,12 +26,14 @@ struct NetHost {
 int64_t net_param_count(int blocks, int F);
 bool net_tc_supported(int F);
 // all pointers are DEVICE pointers; asynchronous on net->ctx->stream
+// `n_dev` (optional, device): actual batch size decided on the GPU (<= n); the kernels read it themselves,
+// so a compacted leaf batch needs no host round trip.
 int net_forward_device(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value,
-                       int out_kind);
+                       int out_kind, const int32_t* n_dev = nullptr);
 int net_forward_simt(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value,
-                     int out_kind);
+                     int out_kind, const int32_t* n_dev);
 int net_forward_tc(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value,
-                   int out_kind);
+                   int out_kind, const int32_t* n_dev);
 
 }  // namespace oth
 

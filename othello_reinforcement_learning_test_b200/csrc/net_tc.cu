@@ -119,8 +119,9 @@ __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off,
 template <int F>
 __global__ void __launch_bounds__(kThreads, 1)
 k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* __restrict__ opp_b, int64_t n,
-         float* __restrict__ policy_out, float* __restrict__ value_out, int out_kind)
+         float* __restrict__ policy_out, float* __restrict__ value_out, int out_kind, const int32_t* __restrict__ n_dev)
 {
+    if (n_dev) { const int64_t nd = *n_dev; n = nd < n ? nd : n; }      // batch size decided on the device
     using C = Cfg<F>;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::offBars);
@@ -279,7 +280,7 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
 bool net_tc_supported(int F) { return F == 64 || F == 128; }
 
 int net_forward_tc(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value,
-                   int out_kind)
+                   int out_kind, const int32_t* n_dev)
 {
     oth_ctx* ctx = net->ctx;
     OTH_REQUIRE(net_tc_supported(net->F), OTH_ERR_UNSUPPORTED, "tcgen05 engine supports num_filters 64 or 128 (got %d)", net->F);
@@ -289,11 +290,11 @@ int net_forward_tc(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, 
     if (net->F == 128) {
         using C = tc::Cfg<128>;
         OTH_CHECK_CUDA(cudaFuncSetAttribute(tc::k_net_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-        tc::k_net_tc<128><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(net->dev, self_b, opp_b, n, policy, value, out_kind);
+        tc::k_net_tc<128><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(net->dev, self_b, opp_b, n, policy, value, out_kind, n_dev);
     } else {
         using C = tc::Cfg<64>;
         OTH_CHECK_CUDA(cudaFuncSetAttribute(tc::k_net_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-        tc::k_net_tc<64><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(net->dev, self_b, opp_b, n, policy, value, out_kind);
+        tc::k_net_tc<64><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(net->dev, self_b, opp_b, n, policy, value, out_kind, n_dev);
     }
     ctx->launches++;
     OTH_CHECK_CUDA(cudaGetLastError());

@@ -34,12 +34,43 @@ k_tree_begin(TreeDev t, const uint64_t* __restrict__ self_b, const uint64_t* __r
     t.root_opp[g] = live ? opp_b[g] : 0ULL;
     t.active[g] = live ? 1 : 0;
     t.n_nodes[g] = 0; t.n_edges[g] = 0; t.n_evals[g] = 0; t.sims_done[g] = 0; t.path_len[g] = 0;
-    t.pending[g] = 0;
+    t.pending[g] = 0; t.eval_slot[g] = -1;
     t.leaf_self[g] = 0ULL; t.leaf_opp[g] = 0ULL; t.leaf_legal[g] = 0ULL;
+    if (g == 0) *t.batch_count = 0;
+}
+
+__device__ __forceinline__ uint32_t cache_index(const TreeDev& t, uint64_t me, uint64_t you)
+{
+    return (uint32_t)(mix64(me ^ mix64(you + 0x9FB21C651E98DF25ULL)) & t.cache_mask);
+}
+
+// A pending leaf asks for its evaluation: table hit, or a request that k_tree_assign resolves, or (cache off)
+// a slot in the compacted batch right away.  Called by one thread per game.
+__device__ __forceinline__ void request_evaluation(const TreeDev& t, int64_t g, uint64_t me, uint64_t you, uint32_t epoch,
+                                                   uint32_t gen)
+{
+    if (t.cache_mask == 0) {
+        const int slot = atomicAdd(t.batch_count, 1);          // order is irrelevant: the network is slot-independent
+        t.batch_self[slot] = me; t.batch_opp[slot] = you; t.eval_slot[g] = slot;
+        t.leaf_src[g] = kSrcSlot;
+        atomicAdd(&t.stats[0], 1ULL);
+        return;
+    }
+    const uint32_t h = cache_index(t, me, you);
+    t.leaf_h[g] = h;
+    const ulonglong2 key = t.c_key[h];
+    if (key.x == me && key.y == you && t.c_gen[h] == gen) {
+        t.leaf_src[g] = kSrcCache;
+        t.c_hit_epoch[h] = epoch;                               // pins the entry for this step
+        atomicAdd(&t.stats[1], 1ULL);
+    } else {
+        t.leaf_src[g] = kSrcMiss;
+        atomicMin(&t.c_owner[h], ((unsigned long long)(~epoch) << 32) | (unsigned long long)(uint32_t)g);
+    }
 }
 
 // First step after begin: every live game asks for its root evaluation (mcts.py:74-75).
-__global__ void __launch_bounds__(kSearchBlock) k_tree_root(TreeDev t, int64_t n)
+__global__ void __launch_bounds__(kSearchBlock) k_tree_root(TreeDev t, int64_t n, uint32_t epoch, uint32_t gen)
 {
     const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (g >= n) return;
@@ -48,9 +79,11 @@ __global__ void __launch_bounds__(kSearchBlock) k_tree_root(TreeDev t, int64_t n
     t.leaf_self[g] = a; t.leaf_opp[g] = b; t.leaf_legal[g] = legal_moves(a, b);
     t.path_len[g] = 0;
     t.pending[g] = 1;
+    request_evaluation(t, g, a, b, epoch, gen);
 }
 
-__global__ void __launch_bounds__(kSearchBlock) k_tree_select(TreeDev t, int64_t n, float c32, uint32_t flags)
+__global__ void __launch_bounds__(kSearchBlock)
+k_tree_select(TreeDev t, int64_t n, float c32, uint32_t flags, uint32_t epoch, uint32_t gen)
 {
     const int64_t g = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -115,21 +148,52 @@ __global__ void __launch_bounds__(kSearchBlock) k_tree_select(TreeDev t, int64_t
             t.leaf_self[g] = me; t.leaf_opp[g] = you; t.leaf_legal[g] = lg;
             t.path_len[g] = depth;
             t.pending[g] = 1;
+            request_evaluation(t, g, me, you, epoch, gen);
         }
     }
 }
 
+// Resolve the misses of this step: the elected game of every table entry gets a batch slot (and will insert),
+// games with the same position share it, colliding positions get a slot of their own.
+__global__ void __launch_bounds__(kSearchBlock) k_tree_assign(TreeDev t, int64_t n)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n || !t.pending[g] || t.leaf_src[g] != kSrcMiss) return;
+    const uint32_t h = t.leaf_h[g];
+    const uint32_t o = (uint32_t)(t.c_owner[h] & 0xFFFFFFFFULL);
+    const uint64_t me = t.leaf_self[g], you = t.leaf_opp[g];
+    if (o != (uint32_t)g && t.leaf_self[o] == me && t.leaf_opp[o] == you) {
+        t.leaf_src[g] = kSrcDedup;
+        t.dedup_of[g] = (int32_t)o;
+        atomicAdd(&t.stats[2], 1ULL);
+        return;
+    }
+    const int slot = atomicAdd(t.batch_count, 1);
+    t.batch_self[slot] = me; t.batch_opp[slot] = you; t.eval_slot[g] = slot;
+    t.leaf_src[g] = (o == (uint32_t)g) ? kSrcOwner : kSrcSlot;
+    atomicAdd(&t.stats[0], 1ULL);
+    if (o != (uint32_t)g) atomicAdd(&t.stats[3], 1ULL);        // different position on the same entry
+}
+
 // Expand the pending leaf of every game with the evaluator's output and back the value up.
 __global__ void __launch_bounds__(kSearchBlock)
-k_tree_expand(TreeDev t, int64_t n, const float* __restrict__ policy, const float* __restrict__ value, int policy_is_raw)
+k_tree_expand(TreeDev t, int64_t n, const float* __restrict__ policy, const float* __restrict__ value, int policy_is_raw,
+              int by_slot, uint32_t epoch, uint32_t gen)
 {
     __shared__ float s_pri[kWarpsPerBlock][68];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t g = blockIdx.x * (int64_t)kWarpsPerBlock + w;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *t.batch_count = 0;      // the evaluator has consumed the batch
     if (g >= n || !t.pending[g]) return;
     const uint64_t lg = t.leaf_legal[g];
+    // where this leaf's evaluation is: the batch slot (own or shared), the table, or (external / hash-net) slot = game
+    const uint8_t how = by_slot ? t.leaf_src[g] : kSrcSlot;
+    int64_t src = g;
+    if (by_slot) src = how == kSrcDedup ? (int64_t)t.eval_slot[t.dedup_of[g]] : (int64_t)t.eval_slot[g];
+    const float* prow = how == kSrcCache ? t.c_priors + (size_t)t.leaf_h[g] * 68 : policy + src * 65;
+    const float leaf_value = how == kSrcCache ? t.c_value[t.leaf_h[g]] : value[src];
     float* pri = s_pri[w];
-    for (int j = lane; j < 65; j += 32) pri[j] = policy[g * 65 + j];
+    for (int j = lane; j < 65; j += 32) pri[j] = prow[j];
     __syncwarp();
     if (policy_is_raw && lane == 0) mask_and_renormalise(pri, lg);        // node.py:71-80
     __syncwarp();
@@ -160,7 +224,7 @@ k_tree_expand(TreeDev t, int64_t n, const float* __restrict__ policy, const floa
         if (depth > 0) {
             const int32_t* path = t.path + g * t.path_cap;
             edge_child[path[depth - 1]] = node_idx;
-            double v = (double)value[g];                                   // value.item(), mcts.py:144
+            double v = (double)leaf_value;                                 // value.item(), mcts.py:144
             for (int i = depth - 1; i >= 0; --i) {
                 const int e = path[i];
                 edge_n[e] += 1;
@@ -170,6 +234,19 @@ k_tree_expand(TreeDev t, int64_t n, const float* __restrict__ policy, const floa
             t.sims_done[g] += 1;
         }
         t.pending[g] = 0;
+    }
+    // the elected evaluator publishes the result, unless somebody read the old entry in this very step
+    if (how == kSrcOwner) {
+        const uint32_t h = t.leaf_h[g];
+        if (t.c_hit_epoch[h] != epoch) {
+            float* dst = t.c_priors + (size_t)h * 68;
+            for (int j = lane; j < 65; j += 32) dst[j] = pri[j];
+            if (lane == 0) {
+                t.c_key[h] = make_ulonglong2(t.leaf_self[g], t.leaf_opp[g]);
+                t.c_value[h] = leaf_value;
+                t.c_gen[h] = gen;
+            }
+        }
     }
 }
 
@@ -314,13 +391,18 @@ int SearchHost::allocate(oth_ctx* c, int64_t games, int sims)
     A(t.n_nodes, G); A(t.n_edges, G); A(t.n_evals, G); A(t.sims_done, G); A(t.path_len, G);
     A(t.pending, G); A(t.active, G);
     A(t.leaf_self, G); A(t.leaf_opp, G); A(t.leaf_legal, G);
+    A(t.batch_self, G); A(t.batch_opp, G); A(t.eval_slot, G); A(t.batch_count, 1);
     A(t.path, G * t.path_cap);
     A(t.node_first, G * t.node_cap); A(t.node_count, G * t.node_cap);
     A(t.edge_n, G * t.edge_cap); A(t.edge_w, G * t.edge_cap); A(t.edge_p, G * t.edge_cap);
     A(t.edge_child, G * t.edge_cap); A(t.edge_action, G * t.edge_cap);
     A(t.eval_policy, G * 65); A(t.eval_value, G);
     A(t.error_flag, 1);
+    A(t.leaf_h, G); A(t.leaf_src, G); A(t.dedup_of, G); A(t.stats, 4);
 #undef A
+    t.cache_mask = 0;
+    OTH_CHECK_CUDA(cudaMemsetAsync(t.stats, 0, 4 * sizeof(unsigned long long), c->stream));
+    OTH_CHECK_CUDA(cudaMemsetAsync(t.leaf_src, 0, G, c->stream));
     OTH_CHECK_CUDA(cudaMemsetAsync(t.error_flag, 0, sizeof(int32_t), c->stream));
     OTH_CHECK_CUDA(cudaMemsetAsync(t.eval_policy, 0, G * 65 * sizeof(float), c->stream));
     OTH_CHECK_CUDA(cudaMemsetAsync(t.eval_value, 0, G * sizeof(float), c->stream));
@@ -354,18 +436,75 @@ int SearchHost::begin(const uint64_t* d_self, const uint64_t* d_opp, const uint8
     return OTH_OK;
 }
 
-int SearchHost::select()
+// The table is only consulted when the built-in network evaluates the leaves (use_cache).
+static inline TreeDev tree_view(const TreeDev& t, bool use_cache)
+{
+    TreeDev v = t;
+    if (!use_cache) v.cache_mask = 0;
+    return v;
+}
+
+int SearchHost::root(bool use_cache)
 {
     TimedLaunch timed(ctx, 1);
-    k_tree_select<<<warp_grid(n), kSearchBlock, 0, ctx->stream>>>(t, n, (float)c_puct, flags);
+    ++epoch;
+    k_tree_root<<<thread_grid(n), kSearchBlock, 0, ctx->stream>>>(tree_view(t, use_cache), n, epoch, generation);
     K_CHECK();
     return OTH_OK;
 }
 
-int SearchHost::expand(const float* d_policy, const float* d_value, bool policy_is_raw)
+int SearchHost::select(bool use_cache)
 {
     TimedLaunch timed(ctx, 1);
-    k_tree_expand<<<warp_grid(n), kSearchBlock, 0, ctx->stream>>>(t, n, d_policy, d_value, policy_is_raw ? 1 : 0);
+    ++epoch;
+    k_tree_select<<<warp_grid(n), kSearchBlock, 0, ctx->stream>>>(tree_view(t, use_cache), n, (float)c_puct, flags, epoch, generation);
+    K_CHECK();
+    return OTH_OK;
+}
+
+int SearchHost::assign()
+{
+    if (!t.cache_mask) return OTH_OK;
+    TimedLaunch timed(ctx, 1);
+    k_tree_assign<<<thread_grid(n), kSearchBlock, 0, ctx->stream>>>(t, n);
+    K_CHECK();
+    return OTH_OK;
+}
+
+int SearchHost::enable_cache(uint64_t capacity)
+{
+    if (cache_on) return OTH_OK;
+    OTH_REQUIRE(capacity >= 1024 && (capacity & (capacity - 1)) == 0, OTH_ERR_ARG, "cache capacity must be a power of two >= 1024");
+    OTH_CHECK_CUDA(cudaSetDevice(ctx->device));
+    int rc = 0;
+    if ((rc = dev_alloc(allocs, &t.c_key, capacity))) return rc;
+    if ((rc = dev_alloc(allocs, &t.c_gen, capacity))) return rc;
+    if ((rc = dev_alloc(allocs, &t.c_value, capacity))) return rc;
+    if ((rc = dev_alloc(allocs, &t.c_priors, capacity * 68))) return rc;
+    if ((rc = dev_alloc(allocs, &t.c_owner, capacity))) return rc;
+    if ((rc = dev_alloc(allocs, &t.c_hit_epoch, capacity))) return rc;
+    OTH_CHECK_CUDA(cudaMemsetAsync(t.c_gen, 0, capacity * sizeof(uint32_t), ctx->stream));
+    OTH_CHECK_CUDA(cudaMemsetAsync(t.c_hit_epoch, 0, capacity * sizeof(uint32_t), ctx->stream));
+    OTH_CHECK_CUDA(cudaMemsetAsync(t.c_owner, 0xFF, capacity * sizeof(unsigned long long), ctx->stream));
+    OTH_CHECK_CUDA(cudaMemsetAsync(t.c_key, 0, capacity * sizeof(ulonglong2), ctx->stream));
+    t.cache_mask = capacity - 1;
+    cache_on = true;
+    return OTH_OK;
+}
+
+int SearchHost::read_stats(unsigned long long out[4], bool reset)
+{
+    OTH_CHECK_CUDA(cudaMemcpyAsync(out, t.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (reset) OTH_CHECK_CUDA(cudaMemsetAsync(t.stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    OTH_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OTH_OK;
+}
+
+int SearchHost::expand(const float* d_policy, const float* d_value, bool policy_is_raw, bool by_slot)
+{
+    TimedLaunch timed(ctx, 1);
+    k_tree_expand<<<warp_grid(n), kSearchBlock, 0, ctx->stream>>>(t, n, d_policy, d_value, policy_is_raw ? 1 : 0, by_slot ? 1 : 0,
+                                                                   epoch, generation);
     K_CHECK();
     return OTH_OK;
 }
@@ -381,7 +520,7 @@ int SearchHost::evaluate(NetHost* net)
     OTH_REQUIRE(net && net->loaded, OTH_ERR_STATE, "search: no network (or weights not loaded) and OTH_FLAG_EVAL_HASHNET not set");
     OTH_REQUIRE(net->ctx == ctx, OTH_ERR_ARG, "search: network belongs to a different context");
     net->evals += (uint64_t)n;
-    return net_forward_device(net, t.leaf_self, t.leaf_opp, n, t.eval_policy, t.eval_value, kOutPriors);
+    return net_forward_device(net, t.batch_self, t.batch_opp, n, t.eval_policy, t.eval_value, kOutPriors, t.batch_count);
 }
 
 int SearchHost::run(NetHost* net, int sims, bool add_noise, uint64_t seed)
@@ -391,18 +530,20 @@ int SearchHost::run(NetHost* net, int sims, bool add_noise, uint64_t seed)
     if (n == 0) return OTH_OK;
     const bool raw = (flags & OTH_FLAG_EVAL_HASHNET) != 0;   // the hash-net emits unmasked pseudo-probabilities
     int rc;
-    k_tree_root<<<thread_grid(n), kSearchBlock, 0, ctx->stream>>>(t, n);
-    K_CHECK();
+    const bool use_cache = !raw && cache_on && (flags & OTH_FLAG_EVAL_CACHE);
+    if ((rc = root(use_cache))) return rc;
+    if (use_cache && (rc = assign())) return rc;
     if ((rc = evaluate(net))) return rc;
-    if ((rc = expand(t.eval_policy, t.eval_value, raw))) return rc;
+    if ((rc = expand(t.eval_policy, t.eval_value, raw, !raw))) return rc;
     if (add_noise && (flags & OTH_FLAG_ROOT_N_SUM)) {
         k_root_noise<<<thread_grid(n), kSearchBlock, 0, ctx->stream>>>(t, n, dir_alpha, dir_eps, seed, nullptr);
         K_CHECK();
     }
     for (int s = 0; s < sims; ++s) {
-        if ((rc = select())) return rc;
+        if ((rc = select(use_cache))) return rc;
+        if (use_cache && (rc = assign())) return rc;
         if ((rc = evaluate(net))) return rc;
-        if ((rc = expand(t.eval_policy, t.eval_value, raw))) return rc;
+        if ((rc = expand(t.eval_policy, t.eval_value, raw, !raw))) return rc;
     }
     awaiting_apply = false;
     return OTH_OK;
@@ -448,6 +589,29 @@ int oth_search_configure(oth_search* s, double c_puct, double dirichlet_alpha, d
 {
     OTH_REQUIRE(s, OTH_ERR_ARG, "oth_search_configure: NULL handle");
     s->c_puct = c_puct; s->dir_alpha = dirichlet_alpha; s->dir_eps = dirichlet_epsilon; s->flags = flags;
+    if ((flags & OTH_FLAG_EVAL_CACHE) && !s->cache_on) {
+        uint64_t want = (uint64_t)s->max_games * (uint64_t)(s->max_sims + 1) * 2, cap = 1 << 16;
+        while (cap < want && cap < (1ULL << 24)) cap <<= 1;
+        int rc = s->enable_cache(cap);
+        if (rc) return rc;
+    }
+    return OTH_OK;
+}
+
+int oth_search_stats(oth_search* s, uint64_t* out4)
+{
+    OTH_REQUIRE(s && out4, OTH_ERR_ARG, "oth_search_stats: NULL argument");
+    OTH_CHECK_CUDA(cudaSetDevice(s->ctx->device));
+    unsigned long long v[4];
+    int rc = s->read_stats(v, true);
+    for (int i = 0; i < 4; ++i) out4[i] = v[i];
+    return rc;
+}
+
+int oth_search_invalidate_cache(oth_search* s)
+{
+    OTH_REQUIRE(s, OTH_ERR_ARG, "oth_search_invalidate_cache: NULL handle");
+    s->invalidate_cache();
     return OTH_OK;
 }
 
@@ -473,13 +637,13 @@ int oth_search_collect(oth_search* s, uint64_t* leaf_self, uint64_t* leaf_opp, u
     const int64_t n = s->n;
     if (n == 0) return OTH_OK;
     if (s->root_pending) {                     // the first collect after begin asks for the roots (mcts.py:74-75)
-        k_tree_root<<<thread_grid(n), kSearchBlock, 0, ctx->stream>>>(s->t, n);
+        int rc = s->root(false);
+        if (rc) return rc;
         s->root_pending = false;
     } else {
-        k_tree_select<<<warp_grid(n), kSearchBlock, 0, ctx->stream>>>(s->t, n, (float)s->c_puct, s->flags);
+        int rc = s->select(false);
+        if (rc) return rc;
     }
-    ctx->launches++;
-    OTH_CHECK_CUDA(cudaGetLastError());
     const cudaMemcpyKind kind = mem == OTH_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     OTH_CHECK_CUDA(cudaMemcpyAsync(leaf_self, s->t.leaf_self, n * 8, kind, ctx->stream));
     OTH_CHECK_CUDA(cudaMemcpyAsync(leaf_opp, s->t.leaf_opp, n * 8, kind, ctx->stream));
@@ -498,7 +662,7 @@ int oth_search_apply(oth_search* s, const float* probs, const float* value, int 
     Staged st(s->ctx, mem);
     const float* p = st.in(probs, n * 65); const float* v = st.in(value, n);
     if (st.failed) return OTH_ERR_CUDA;
-    int rc = s->expand(p, v, true);
+    int rc = s->expand(p, v, true, false);
     if (rc) return rc;
     s->awaiting_apply = false;
     return st.finish();

@@ -18,7 +18,25 @@ struct TreeDev {
     uint64_t *root_self, *root_opp;
     int32_t *n_nodes, *n_edges, *n_evals, *sims_done, *path_len;
     uint8_t *pending, *active;
-    uint64_t *leaf_self, *leaf_opp, *leaf_legal;   // evaluation batch (slot = game)
+    uint64_t *leaf_self, *leaf_opp, *leaf_legal;   // pending leaf of every game
+    // compacted evaluation batch: only leaves that really need the network (no terminal leaves, no idle slots)
+    uint64_t *batch_self, *batch_opp;
+    int32_t *eval_slot;       // [games] index into the batch / eval_policy / eval_value, -1 = none
+    int32_t *batch_count;     // device-side counter, reset by k_tree_expand
+    // position-keyed evaluation cache + same-step dedup (optional; result-transparent because the
+    // network's output does not depend on where in a batch a position sits).  Direct-mapped on a hash
+    // of (self, opp); entries carry the masked priors and the value exactly as the network wrote them.
+    uint64_t cache_mask;             // capacity - 1; 0 = cache off
+    ulonglong2* c_key;               // (self, opp)
+    uint32_t* c_gen;                 // entry valid iff == current generation (bumped when the weights change)
+    float* c_value;
+    float* c_priors;                 // [capacity][68]
+    unsigned long long* c_owner;     // (~epoch << 32 | game): atomicMin elects one evaluator per entry and step
+    uint32_t* c_hit_epoch;           // step in which the entry was last read (no overwrite in that step)
+    uint32_t* leaf_h;                // [games] table index of the pending leaf
+    uint8_t* leaf_src;               // [games] kSrc*
+    int32_t* dedup_of;               // [games] game whose evaluation this leaf shares
+    unsigned long long* stats;       // [0] network positions, [1] cache hits, [2] same-step duplicates, [3] hash collisions
     int32_t* path;            // [games][path_cap] edge indices of the pending simulation
     // per node
     int32_t* node_first;      // first edge
@@ -35,6 +53,12 @@ struct TreeDev {
     int32_t* error_flag;      // != 0: a pool overflowed
 };
 
+constexpr uint8_t kSrcSlot = 0;      // own slot in the evaluation batch (cache off, or colliding entry: no insert)
+constexpr uint8_t kSrcOwner = 1;     // own slot, and inserts the result into the table
+constexpr uint8_t kSrcCache = 2;     // table hit
+constexpr uint8_t kSrcDedup = 3;     // same position as another game's leaf in this step
+constexpr uint8_t kSrcMiss = 4;      // (between select and assign) wants an evaluation
+
 struct SearchHost {
     oth_ctx* ctx = nullptr;
     int64_t max_games = 0, n = 0;
@@ -45,16 +69,23 @@ struct SearchHost {
     TreeDev t{};
     std::vector<void*> allocs;
     uint64_t total_evals = 0;
+    uint32_t epoch = 0, generation = 1;
+    bool cache_on = false;
 
     int allocate(oth_ctx* c, int64_t games, int sims);
     void release();
     // device-pointer, asynchronous building blocks (n = live games, all on ctx->stream)
     int begin(const uint64_t* d_self, const uint64_t* d_opp, const uint8_t* d_active, int64_t n_games);
-    int select();                                              // one descent per game -> leaf batch / terminal backup
-    int expand(const float* d_policy, const float* d_value, bool policy_is_raw);   // expand pending leaves + backup
+    int root(bool use_cache);                                  // every live game requests its root evaluation
+    int select(bool use_cache);                                // one descent per game -> leaf batch / terminal backup
+    int expand(const float* d_policy, const float* d_value, bool policy_is_raw, bool by_slot);   // expand pending leaves + backup
     int evaluate(NetHost* net);                                // leaf batch -> t.eval_policy (priors) / t.eval_value
     int run(NetHost* net, int sims, bool add_noise, uint64_t seed);
     int check_overflow();
+    int enable_cache(uint64_t capacity_pow2);                  // allocate the evaluation cache (once)
+    void invalidate_cache() { ++generation; }                  // weights changed / new campaign
+    int assign();                                              // resolve misses into batch slots / duplicates
+    int read_stats(unsigned long long out[4], bool reset);
 };
 
 }  // namespace oth

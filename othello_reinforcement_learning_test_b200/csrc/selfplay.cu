@@ -139,6 +139,7 @@ struct SelfPlayHost {
     unsigned long long* h_counters = nullptr;   // pinned
     int64_t last_samples = 0;
     uint64_t moves_played = 0;
+    unsigned long long last_stats[4] = {0, 0, 0, 0};
 
     int create(oth_ctx* c, const oth_selfplay_config* cf);
     void release();
@@ -153,6 +154,11 @@ int SelfPlayHost::create(oth_ctx* c, const oth_selfplay_config* cf)
     if (rc) return rc;
     search.c_puct = cfg.c_puct; search.dir_alpha = cfg.dirichlet_alpha; search.dir_eps = cfg.dirichlet_epsilon;
     search.flags = cfg.flags;
+    if (cfg.flags & OTH_FLAG_EVAL_CACHE) {
+        uint64_t want = (uint64_t)cfg.concurrent_games * 2048ULL, cap = 1 << 16;
+        while (cap < want && cap < (1ULL << 24)) cap <<= 1;
+        if ((rc = search.enable_cache(cap))) return rc;
+    }
     d.slots = cfg.concurrent_games;
     const size_t S = (size_t)d.slots;
     auto grab = [&](void** p, size_t bytes) {
@@ -200,6 +206,12 @@ int SelfPlayHost::run(NetHost* net, int64_t num_episodes, int64_t* n_samples, in
         OTH_CHECK_CUDA(cudaMalloc((void**)&d.out, (size_t)need * sizeof(oth_sample)));
         d.out_cap = need;
     }
+    search.invalidate_cache();          // a campaign starts cold: the weights usually changed since the last one
+    {
+        unsigned long long dummy[4];
+        int rc0 = search.read_stats(dummy, true);
+        if (rc0) return rc0;
+    }
     const int grid_t = (int)((d.slots + 255) / 256), grid_w = (int)((d.slots + 7) / 8);
     k_sp_reset<<<grid_t, 256, 0, ctx->stream>>>(d, num_episodes);
     ctx->launches++;
@@ -225,6 +237,7 @@ int SelfPlayHost::run(NetHost* net, int64_t num_episodes, int64_t* n_samples, in
     }
     int rc = search.check_overflow();
     if (rc) return rc;
+    if ((rc = search.read_stats(last_stats, false))) return rc;
     last_samples = (int64_t)h_counters[2];
     if (n_samples) *n_samples = last_samples;
     if (n_evals) *n_evals = (int64_t)h_counters[4];
@@ -265,6 +278,13 @@ int oth_selfplay_run(oth_selfplay* sp, oth_net* net, int64_t num_episodes, int64
 {
     OTH_REQUIRE(sp, OTH_ERR_ARG, "oth_selfplay_run: NULL handle");
     return sp->run(net, num_episodes, n_samples_out, n_evals_out);
+}
+
+int oth_selfplay_stats(oth_selfplay* sp, uint64_t* out4)
+{
+    OTH_REQUIRE(sp && out4, OTH_ERR_ARG, "oth_selfplay_stats: NULL argument");
+    for (int i = 0; i < 4; ++i) out4[i] = sp->last_stats[i];
+    return OTH_OK;
 }
 
 int oth_selfplay_fetch(oth_selfplay* sp, oth_sample* out, int64_t capacity, int mem)

@@ -63,6 +63,11 @@ class TreeSearch:
         check(self.ctx.lib.oth_search_results(self.handle, ptr(v), ptr(q), ptr(e), MEM_HOST))
         return v, q, e
 
+    def stats(self) -> dict:
+        v = (C.c_uint64 * 4)()
+        check(self.ctx.lib.oth_search_stats(self.handle, v))
+        return {"nn_positions": int(v[0]), "cache_hits": int(v[1]), "same_step_duplicates": int(v[2]), "hash_collisions": int(v[3])}
+
     def policy(self, temperature: float) -> np.ndarray:
         p = np.empty((self.n, 65), np.float32)
         check(self.ctx.lib.oth_search_policy(self.handle, float(temperature), ptr(p), MEM_HOST))
@@ -91,13 +96,15 @@ class MCTS:
 
     def __init__(self, model, device, c_puct: float = 1.0, dirichlet_alpha: float = 0.3,
                  dirichlet_epsilon: float = 0.25, *, evaluator: str = "auto", root_n_sum: bool = False,
-                 q_canonical: bool = False, engine: str | None = None, ctx: Context | None = None):
+                 q_canonical: bool = False, engine: str | None = None, eval_cache: bool = False,
+                 ctx: Context | None = None):
         self.model = model
         self.device = device
         self.c_puct = c_puct
         self.dirichlet_alpha = dirichlet_alpha
         self.dirichlet_epsilon = dirichlet_epsilon
         self.root_n_sum, self.q_canonical = root_n_sum, q_canonical
+        self.eval_cache = eval_cache          # position-keyed evaluation cache (native evaluator only; same results)
         self._ctx = ctx
         self._engine = engine
         self._tree: TreeSearch | None = None
@@ -130,6 +137,8 @@ class MCTS:
             f |= _lib.FLAG_Q_CANONICAL
         if self.evaluator == "hashnet":
             f |= _lib.FLAG_EVAL_HASHNET
+        if self.eval_cache and self.evaluator == "native":
+            f |= _lib.FLAG_EVAL_CACHE
         return f
 
     def _tree_for(self, n: int, sims: int) -> TreeSearch:
@@ -146,8 +155,8 @@ class MCTS:
         from .net import InferenceNet
         if self._net is None:
             self._net = InferenceNet.from_module(self.model, self._context(), self._engine)
-        else:
-            self._net.sync_from(self.model)
+        elif self._net.sync_from(self.model) and self._tree is not None:
+            check(self._context().lib.oth_search_invalidate_cache(self._tree.handle))   # new weights: cached outputs are stale
         return self._net
 
     def _call_model(self, leaf_self, leaf_opp):

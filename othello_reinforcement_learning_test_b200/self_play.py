@@ -68,6 +68,10 @@ class SelfPlayEngine:
         ns, ne = C.c_int64(0), C.c_int64(0)
         check(self.ctx.lib.oth_selfplay_run(self.handle, net_handle, int(num_episodes), C.byref(ns), C.byref(ne)))
         self.last_n_evals = int(ne.value)
+        st = (C.c_uint64 * 4)()
+        check(self.ctx.lib.oth_selfplay_stats(self.handle, st))
+        self.last_stats = {"nn_positions": int(st[0]), "cache_hits": int(st[1]), "same_step_duplicates": int(st[2]),
+                           "hash_collisions": int(st[3])}
         out = np.empty(int(ns.value), _lib.SAMPLE_DTYPE)
         check(self.ctx.lib.oth_selfplay_fetch(self.handle, ptr(out), out.size, MEM_HOST))
         return out
@@ -98,7 +102,8 @@ class ParallelSelfPlayWorker:
                  num_parallel_games: int = 8, c_puct: float = 1.0, dirichlet_alpha: float = 0.3,
                  dirichlet_epsilon: float = 0.25, *, concurrent_games: int | None = None, evaluator: str = "auto",
                  winner_black: bool = False, root_n_sum: bool = False, q_canonical: bool = False,
-                 engine: str | None = None, seed: int | None = None, verbose: bool = True, ctx: Context | None = None):
+                 engine: str | None = None, seed: int | None = None, verbose: bool = True, eval_cache: bool = True,
+                 ctx: Context | None = None):
         self.board_class = board_class
         self.num_simulations = num_simulations
         self.temperature_threshold = temperature_threshold
@@ -108,7 +113,7 @@ class ParallelSelfPlayWorker:
         self.concurrent_games = concurrent_games
         self.batch_mcts = BatchMCTS(model=model, device=device, c_puct=c_puct, dirichlet_alpha=dirichlet_alpha,
                                     dirichlet_epsilon=dirichlet_epsilon, evaluator=evaluator, root_n_sum=root_n_sum,
-                                    q_canonical=q_canonical, engine=engine, ctx=ctx)
+                                    q_canonical=q_canonical, engine=engine, eval_cache=eval_cache, ctx=ctx)
         self.winner_black = winner_black
         self.seed = seed
         self.verbose = verbose
@@ -147,7 +152,7 @@ class ParallelSelfPlayWorker:
         samples = eng.run(net, num_episodes)
         dt = time.time() - t0
         self.last_stats = {"episodes": num_episodes, "samples": int(samples.size), "seconds": dt,
-                           "nn_evals": eng.last_n_evals, "concurrent_games": eng.cfg.concurrent_games}
+                           "nn_evals": eng.last_n_evals, "concurrent_games": eng.cfg.concurrent_games, **eng.last_stats}
         return samples
 
     def execute_episodes(self, num_episodes: int, add_dirichlet_noise: bool = True) -> List[Sample]:

@@ -64,3 +64,33 @@ def test_selfplay_with_the_network_through_the_reference_api(ctx):
     assert m.get_best_action(b, 50) in b.get_legal_moves()
     ev = m.get_action_evaluations(b, 20)
     assert ev.dtype == np.int32 and ev.shape == (65,) and ((ev >= 0) & (ev <= 100)).all()
+
+
+def test_eval_cache_and_dedup_are_result_transparent(ctx, golden_games):
+    """Position-keyed cache + same-step dedup must not change a single visit count or sample."""
+    import othello_reinforcement_learning_test_b200 as pkg
+    from othello_reinforcement_learning_test_b200.net import OthelloResNet
+    torch.manual_seed(42)
+    model = OthelloResNet(5, 64).eval()
+    kw = dict(num_simulations=30, temperature_threshold=15, num_parallel_games=16, seed=21, concurrent_games=96, verbose=False)
+    a = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, "cuda", eval_cache=False, **kw)
+    b = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, "cuda", eval_cache=True, **kw)
+    sa = a.execute_episodes_packed(160); sb = b.execute_episodes_packed(160)          # 96 slots, 160 episodes: refill
+    sa = sa[np.lexsort((sa["ply"], sa["game"]))]; sb = sb[np.lexsort((sb["ply"], sb["game"]))]
+    assert sa.size == sb.size and sa.tobytes() == sb.tobytes()
+    st_a, st_b = a.last_stats, b.last_stats
+    assert st_a["nn_evals"] == st_b["nn_evals"]                                       # expansions: same searches
+    assert st_a["nn_positions"] == st_a["nn_evals"] and st_a["cache_hits"] == 0
+    assert st_b["nn_positions"] + st_b["cache_hits"] + st_b["same_step_duplicates"] == st_b["nn_evals"]
+    assert st_b["cache_hits"] > 0.1 * st_b["nn_evals"] and st_b["same_step_duplicates"] > 0
+    # second campaign on the same worker starts from an emptied cache and still agrees with the uncached engine
+    sa2 = a.execute_episodes_packed(40); sb2 = b.execute_episodes_packed(40)
+    sa2 = sa2[np.lexsort((sa2["ply"], sa2["game"]))]; sb2 = sb2[np.lexsort((sb2["ply"], sb2["game"]))]
+    assert sa2.tobytes() == sb2.tobytes()
+    # plain searches: transpositions inside one search hit the table too
+    S, O = _positions(golden_games, 64, 17)
+    m0 = pkg.MCTS(model, "cuda", c_puct=1.5); m1 = pkg.MCTS(model, "cuda", c_puct=1.5, eval_cache=True)
+    v0, q0, e0 = m0.search_arrays(S, O, 100); v1, q1, e1 = m1.search_arrays(S, O, 100)
+    assert np.array_equal(v0, v1) and np.array_equal(q0, q1) and np.array_equal(e0, e1)
+    st = m1._tree.stats()
+    assert st["nn_positions"] + st["cache_hits"] + st["same_step_duplicates"] == int(e1.sum())
