@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one self-play campaign: G concurrent games per GPU (default 2368 = 16 x 148 SMs) started
+A "step" is one self-play campaign: G concurrent games per GPU (default 18944 = 128 x 148 SMs) started
 from the initial position and played to completion with the device-resident engine
 (ParallelSelfPlayWorker / oth_selfplay_run): per ply one search of 1 + 50 leaf evaluations per game
 (select -> tcgen05 ResNet -> expand/backup), move choice, trajectory recording, labelling.
@@ -278,9 +278,17 @@ def run_b200(args):
     useful_evals = float(cache_stats[0])       # positions the network really evaluated on this rank (compacted, de-duplicated)
     achieved = useful_evals * fpp / (net_ms / 1000.0) / 1e12 if net_ms > 0 else 0.0
     launched_positions = useful_evals
+    traffic = None            # dram read+write bytes per launch of the kernel, from the committed ncu --set full capture
+    try:
+        for ln in open(os.path.join(ROOT, "profiles", "r01_prof_net_tc.txt")):
+            if "dram__bytes_read.sum " in ln and "Mbyte" in ln:
+                traffic = int(float(ln.split()[1]) * 1e6)
+                break
+    except OSError:
+        pass
     roof = {"bound": "tensor", "kernel": "k_net_tc" if args.engine != "simt" else "k_net_simt", "achieved": achieved,
             "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-            "traffic": None, "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
+            "traffic": traffic, "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
             "flop_per_position": fpp, "useful_positions": int(useful_evals), "launched_positions": int(launched_positions),
             "kernel_ms_total": net_ms, "kernel_launches": int(net_launches),
             "kernel_share_of_step": net_ms / total_ms if total_ms else None,
@@ -316,7 +324,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--games", type=int, default=2368, help="concurrent games per GPU = games per step per GPU")
+    ap.add_argument("--games", type=int, default=18944, help="concurrent games per GPU = games per step per GPU (128 x 148 SMs)")
     ap.add_argument("--sims", type=int, default=50)
     ap.add_argument("--blocks", type=int, default=10)
     ap.add_argument("--filters", type=int, default=128)

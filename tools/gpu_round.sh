@@ -8,11 +8,13 @@ timeout 1500 python -m pytest tests -q -m gpu -x --tb=short > "$OUT/pytest_gpu.l
 timeout 300 python __graft_entry__.py smoke > "$OUT/smoke.log" 2>&1; echo "smoke rc=$?" | tee -a "$OUT/summary.txt"
 timeout 900 python bench.py ${BENCH_ARGS:-} > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?" | tee -a "$OUT/summary.txt"
 if [ "${NCU:-1}" = "1" ]; then
-  NCU_CMD="python bench.py --steps 1 --warmup 0 --games 592 --no-cpu-baseline"
+  NCU_CMD="python bench.py --steps 1 --warmup 0 --games 2368 --no-cpu-baseline"
   timeout 600 $NCU_CMD > "$OUT/ncu_plain.log" 2>&1 && \
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file "$OUT/launches.csv" $NCU_CMD > "$OUT/ncu_launches.log" 2>&1
   echo "ncu launches rc=$?" | tee -a "$OUT/summary.txt"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_net_tc -s 60 -c 2 -o "$OUT/prof_net_tc" -f $NCU_CMD > "$OUT/ncu_full.log" 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_net_tc -s 400 -c 2 -o "$OUT/prof_net_tc" -f $NCU_CMD > "$OUT/ncu_full.log" 2>&1
   echo "ncu full rc=$?" | tee -a "$OUT/summary.txt"
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_tree_select|k_tree_expand|k_tree_assign|k_playouts" -s 300 -c 8 -o "$OUT/prof_tree" -f $NCU_CMD > "$OUT/ncu_tree.log" 2>&1
+  echo "ncu tree rc=$?" | tee -a "$OUT/summary.txt"
 fi
 tail -n 6 "$OUT/pytest_gpu.log"; cat "$OUT/smoke.log" | tail -3; cat "$OUT/bench.json"; tail -5 "$OUT/bench.err"; cat "$OUT/summary.txt"
