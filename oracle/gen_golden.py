@@ -316,7 +316,7 @@ def gen_net(ref, out, rows):
         assert np.array_equal(_board(ref, int(S[i]), int(O[i])).get_tensor_input(), x[i].numpy())
     res = {"self_b": S, "opp_b": O}
     for nb, nf, seed in [(2, 32, 5), (5, 64, 6), (10, 128, 7)]:
-        sd = net_oracle.make_state_dict(nb, nf, seed)
+        sd = net_oracle.make_state_dict(nb, nf, seed, gain=net_oracle.SYNTH_GAIN[(nb, nf)])
         m = ref.OthelloResNet(nb, nf); m.load_state_dict(sd); m.eval()
         with torch.no_grad():
             lp, v = m(x)
@@ -341,6 +341,13 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     ref = refload.reference_python()
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+    if only == "net":          # the network fixture alone (the positions come from the committed ref_games.npz)
+        g = np.load(os.path.join(OUT, "ref_games.npz"))
+        rows = [(int(a), int(b), int(c), int(d), int(e), int(f), int(t), int(w)) for a, b, c, d, e, f, t, w in
+                zip(g["game"], g["self_b"], g["opp_b"], g["move_count"], g["legal"], g["action"], g["terminal"], g["winner"])]
+        gen_net(ref, OUT, rows)
+        return
     gen_bitboard(ref, OUT)
     rows = gen_games(ref, OUT)
     gen_mcts(ref, OUT, rows)

@@ -18,6 +18,10 @@ import torch.nn.functional as F
 
 BN_EPS = 1e-5  # nn.BatchNorm2d default, net.py:25
 
+# conv gain of the synthetic fixture weights per network shape: the deep net is toned down so that its policy is not
+# saturated (gain 1.0 gives p_max 0.99, where bf16 rounding noise alone moves single probabilities by > 1e-2)
+SYNTH_GAIN = {(2, 32): 1.0, (5, 64): 1.0, (10, 128): 0.7}
+
 
 def state_dict_keys(num_blocks: int):
     """Key order of the reference module's state_dict (SURVEY 8(a) R-NN)."""

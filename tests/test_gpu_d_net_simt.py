@@ -17,7 +17,7 @@ TOL_EMULATED = 3e-3
 # The synthetic 10x128 weights are deliberately hot (peaked policies, |logit| ~ 20): two bf16 pipelines that
 # differ only in fp32 accumulation order already drift ~1e-2 apart on single probabilities after 21 layers
 # (measured: 1.2e-2 for both engines); the mean drift stays ~1e-4.
-TOL_EMULATED_HOT_MAX = 4e-2
+TOL_EMULATED_HOT_MAX = 2.5e-2
 TOL_EMULATED_HOT_MEAN = 1e-3
 
 
@@ -42,7 +42,7 @@ def _check(net, sd, S, O, logp_ref, v_ref, tol_fp32, hot=False):
 def test_simt_engine_synthetic_weights(ctx, golden_net, nb, nf, seed):
     from othello_reinforcement_learning_test_b200.net import InferenceNet
     g = golden_net
-    sd = net_oracle.make_state_dict(nb, nf, seed)
+    sd = net_oracle.make_state_dict(nb, nf, seed, gain=net_oracle.SYNTH_GAIN[(nb, nf)])
     net = InferenceNet(nb, nf, ctx, engine="simt")
     net.load_state_dict(sd)
     _check(net, sd, g["self_b"], g["opp_b"], g[f"logp_{nb}x{nf}_s{seed}"], g[f"value_{nb}x{nf}_s{seed}"], TOL_FP32_SYNTH,

@@ -133,7 +133,7 @@ def test_selfplay_traces(golden_selfplay, tag):
 @pytest.mark.parametrize("nb,nf,seed", [(2, 32, 5), (5, 64, 6), (10, 128, 7)])
 def test_net_fp32_restatement_matches_reference_module_outputs(golden_net, nb, nf, seed):
     g = golden_net
-    sd = net_oracle.make_state_dict(nb, nf, seed)
+    sd = net_oracle.make_state_dict(nb, nf, seed, gain=net_oracle.SYNTH_GAIN[(nb, nf)])
     x = net_oracle.boards_to_tensor(g["self_b"], g["opp_b"])
     torch.set_num_threads(4)
     lp, v = net_oracle.forward_fp32(sd, x)
