@@ -92,6 +92,13 @@ int oth_random_playouts(oth_ctx* ctx, int64_t n_games, uint64_t seed, int64_t* t
                         int64_t* winner_hist_out, uint64_t* final_self, uint64_t* final_opp,
                         int32_t* plies, int mem);
 
+/* baseline players of the arena, batched: RandomPlayer.get_action (src/eval/players.py:60-67; salt[i] individualises
+ * the draw, NULL = index) and GreedyPlayer.get_action (players.py:79-113, scoring rule exactly as written there) */
+int oth_choose_random(oth_ctx* ctx, const uint64_t* self_b, const uint64_t* opp_b, const uint64_t* salt, uint64_t seed,
+                      int32_t* action_out, int64_t n, int mem);
+int oth_choose_greedy(oth_ctx* ctx, const uint64_t* self_b, const uint64_t* opp_b, const int32_t* move_count,
+                      int32_t* action_out, int64_t n, int mem);
+
 /* ---- network: src/model/net.py OthelloResNet ------------------------------------ */
 #define OTH_NET_ENGINE_TCGEN05 0 /* bf16 tcgen05/TMEM implicit-GEMM trunk (product path) */
 #define OTH_NET_ENGINE_SIMT 1    /* CUDA-core validation kernel, same rounding points */
@@ -185,6 +192,19 @@ int oth_selfplay_stats(oth_selfplay* sp, uint64_t* out4);
 int oth_selfplay_fetch(oth_selfplay* sp, oth_sample* out, int64_t capacity, int mem);
 /* device pointer + count of the last run's samples (for NCCL all-gather without a host hop) */
 int oth_selfplay_samples_device(oth_selfplay* sp, const oth_sample** dev_ptr_out, int64_t* count_out);
+
+/* ---- replay buffer: src/train/buffer.py ReplayBuffer ------------------------------------------------ */
+typedef struct oth_replay oth_replay;
+int oth_replay_create(oth_ctx* ctx, int64_t max_size, oth_replay** out);       /* ReplayBuffer(max_size), buffer.py:23-31 */
+int oth_replay_destroy(oth_replay* r);
+int64_t oth_replay_size(const oth_replay* r);                                  /* __len__, buffer.py:86-88 */
+int oth_replay_clear(oth_replay* r);                                           /* clear, buffer.py:90-92 */
+/* add / deque(maxlen).append of n packed samples (HOST or DEVICE, e.g. oth_selfplay_samples_device), buffer.py:33-45 */
+int oth_replay_add(oth_replay* r, const oth_sample* samples, int64_t n, int mem);
+/* sample (buffer.py:58-84) for caller-drawn logical indices (0 = oldest): states f32 [n,3,8,8], policies f32 [n,65],
+ * values f32 [n] (= [n,1]); idx and outputs live where `mem` says */
+int oth_replay_gather(oth_replay* r, const int64_t* idx, int64_t n, float* states, float* policies, float* values, int mem);
+int oth_replay_value_stats(oth_replay* r, double* mean_out, double* std_out);  /* get_statistics, buffer.py:102-123 */
 
 /* ---- diagnostics ---------------------------------------------------------------------- */
 /* One accumulation chain of tcgen05.mma (M=128, N=n, K=16*k_steps, bf16 -> fp32) over a caller

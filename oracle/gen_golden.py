@@ -14,6 +14,8 @@ tests/golden/:
   selfplay_ref.npz   deterministic (threshold 0) self-play traces, batched + serial
   net_ref.npz        reference OthelloResNet fp32 outputs for synthetic weights
                      + checksum of the torch.manual_seed(42) initialisation
+  replay_ref.npz     reference ReplayBuffer: seeded minibatches and statistics
+  arena_ref.npz      reference Arena results with deterministic players
 
 Usage:  python -m oracle.gen_golden
 """
@@ -337,6 +339,64 @@ def gen_net(ref, out, rows):
     print("net_ref written")
 
 
+def replay_fixture_data(games):
+    """Deterministic training tuples built from the committed reference games (shared with the tests)."""
+    rng = np.random.default_rng(99)
+    live = np.flatnonzero(games["terminal"] == 0)[:700]
+    S, O = games["self_b"][live], games["opp_b"][live]
+    states = cref.tensor_input_batch(S, O)
+    data = []
+    for i in range(len(live)):
+        legal = cref.legal_list(int(S[i]), int(O[i]))
+        sims = int(rng.choice([25, 50, 100]))
+        counts = rng.multinomial(sims, np.ones(len(legal)) / len(legal))
+        pol = np.zeros(65, np.float32)
+        pol[legal] = counts.astype(np.float32) / np.float32(sims)
+        data.append((states[i], pol, float(rng.integers(-1, 2))))
+    return data
+
+
+def gen_replay(ref, out):
+    import random
+    games = dict(np.load(os.path.join(out, "ref_games.npz")))
+    data = replay_fixture_data(games)
+    buf = ref.ReplayBuffer(max_size=500)                     # smaller than the data: the oldest 200 fall out
+    buf.add(data[:300]); buf.add(data[300:])
+    random.seed(5)
+    st, po, va = buf.sample(48)
+    random.seed(6)
+    st2, po2, va2 = buf.sample(500)
+    stats = buf.get_statistics()
+    np.savez_compressed(os.path.join(out, "replay_ref.npz"), states=st, policies=po, values=va,
+                        all_states_sum=st2.sum(axis=0), all_policies=po2, all_values=va2,
+                        stats=np.array([stats["size"], stats["max_size"], stats["fill_rate"], stats["value_mean"], stats["value_std"]]))
+    print("replay_ref written", st.shape, po.shape, va.shape, stats)
+
+
+def gen_arena(ref, out):
+    """Reference Arena with deterministic players: Greedy vs Greedy, hash-net MCTS vs Greedy."""
+    res = {}
+    arena = ref.Arena(verbose=False)
+
+    def pack(results):
+        return np.array([[r.winner, r.player1_score, r.player2_score, r.num_moves] for r in results], np.int32)
+    res["greedy_vs_greedy"] = pack(arena.play_matches(ref.GreedyPlayer("A"), ref.GreedyPlayer("B"), num_games=4))
+    for sims in (8, 25):
+        mp = ref.MCTSPlayer(None, torch.device("cpu"), num_simulations=sims)
+
+        def pred(board_tensor):
+            a, b = _bits_from_tensor(board_tensor)
+            p, v = cref.hashnet(int(a[0]), int(b[0]))
+            return p, torch.tensor([[v]], dtype=torch.float32)
+        mp.mcts._predict = pred
+        res[f"mcts{sims}_vs_greedy"] = pack(arena.play_matches(mp, ref.GreedyPlayer("G"), num_games=4))
+        res[f"greedy_vs_mcts{sims}"] = pack(arena.play_matches(ref.GreedyPlayer("G"), mp, num_games=2, alternate_colors=False))
+    ev = ref.evaluate_player(ref.GreedyPlayer("A"), ref.GreedyPlayer("B"), num_games=6, verbose=False)
+    res["evaluate_greedy"] = np.array([ev["win_rate"], ev["avg_score"], ev["avg_moves"]])
+    np.savez_compressed(os.path.join(out, "arena_ref.npz"), **res)
+    print("arena_ref written", {k: v.tolist() for k, v in res.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -348,11 +408,19 @@ def main():
                 zip(g["game"], g["self_b"], g["opp_b"], g["move_count"], g["legal"], g["action"], g["terminal"], g["winner"])]
         gen_net(ref, OUT, rows)
         return
+    if only == "replay":
+        gen_replay(ref, OUT)
+        return
+    if only == "arena":
+        gen_arena(ref, OUT)
+        return
     gen_bitboard(ref, OUT)
     rows = gen_games(ref, OUT)
     gen_mcts(ref, OUT, rows)
     gen_selfplay(ref, OUT)
     gen_net(ref, OUT, rows)
+    gen_replay(ref, OUT)
+    gen_arena(ref, OUT)
     print("golden fixtures written to", OUT)
 
 

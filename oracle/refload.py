@@ -79,4 +79,9 @@ def reference_python():
     ns.ParallelSelfPlayWorker = psp.ParallelSelfPlayWorker
     ns.SelfPlayWorker = importlib.import_module("src.train.self_play").SelfPlayWorker
     ns.OthelloResNet = importlib.import_module("src.model.net").OthelloResNet
+    ns.ReplayBuffer = importlib.import_module("src.train.buffer").ReplayBuffer
+    arena = importlib.import_module("src.eval.arena")
+    players = importlib.import_module("src.eval.players")
+    ns.Arena, ns.evaluate_player = arena.Arena, arena.evaluate_player
+    ns.GreedyPlayer, ns.RandomPlayer, ns.MCTSPlayer = players.GreedyPlayer, players.RandomPlayer, players.MCTSPlayer
     return ns

@@ -9,6 +9,8 @@ The reference's API surface for the path bitboard -> MCTS -> ResNet leaf evaluat
     OthelloResNet, InferenceNet          src/model/net.py
     SelfPlayWorker, ParallelSelfPlayWorker, create_parallel_self_play_worker
                                          src/train/self_play.py, src/train/parallel_self_play.py
+    ReplayBuffer                         src/train/buffer.py (device-resident, packed samples)
+    BatchArena, Random/Greedy/MCTSPlayer src/eval/arena.py, src/eval/players.py (all games of a match in flight together)
     dropin.install()                     makes `from src.cython.bitboard import OthelloBitboard`
                                          etc. resolve to this package
 
@@ -22,12 +24,15 @@ _lib.load()   # fail loudly, right here, if the CUDA library is missing
 from .bitboard import BoardBatch, OthelloBitboard   # noqa: E402
 from .mcts import MCTS, BatchMCTS   # noqa: E402
 from .net import InferenceNet, OthelloResNet, create_model   # noqa: E402
+from .buffer import PrioritizedReplayBuffer, ReplayBuffer   # noqa: E402
+from .arena import BatchArena, GreedyPlayer, MatchResult, MCTSPlayer, RandomPlayer, evaluate_player   # noqa: E402
 from .self_play import (ParallelSelfPlayWorker, SelfPlayWorker, augment_data_with_symmetries,   # noqa: E402
                         create_parallel_self_play_worker)
 
 __all__ = [
     "Context", "OthelloB200Error", "OthelloBitboard", "BoardBatch", "MCTS", "BatchMCTS", "OthelloResNet",
     "InferenceNet", "create_model", "SelfPlayWorker", "ParallelSelfPlayWorker", "create_parallel_self_play_worker",
-    "augment_data_with_symmetries",
+    "augment_data_with_symmetries", "ReplayBuffer", "PrioritizedReplayBuffer", "BatchArena", "MatchResult", "RandomPlayer",
+    "GreedyPlayer", "MCTSPlayer", "evaluate_player",
 ]
 __version__ = "0.1.0"

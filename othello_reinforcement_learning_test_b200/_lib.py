@@ -64,6 +64,15 @@ _PROTOS = {
     "oth_tensor_input": (C.c_int, [_p, _p, _p, _p, _i64, C.c_int]),
     "oth_perft": (C.c_int, [_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
     "oth_random_playouts": (C.c_int, [_p, _i64, C.c_uint64, C.POINTER(_i64), C.POINTER(_i64), _p, _p, _p, C.c_int]),
+    "oth_choose_random": (C.c_int, [_p, _p, _p, _p, C.c_uint64, _p, _i64, C.c_int]),
+    "oth_choose_greedy": (C.c_int, [_p, _p, _p, _p, _p, _i64, C.c_int]),
+    "oth_replay_create": (C.c_int, [_p, _i64, C.POINTER(_p)]),
+    "oth_replay_destroy": (C.c_int, [_p]),
+    "oth_replay_size": (_i64, [_p]),
+    "oth_replay_clear": (C.c_int, [_p]),
+    "oth_replay_add": (C.c_int, [_p, _p, _i64, C.c_int]),
+    "oth_replay_gather": (C.c_int, [_p, _p, _i64, _p, _p, _p, C.c_int]),
+    "oth_replay_value_stats": (C.c_int, [_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "oth_net_create": (C.c_int, [_p, C.c_int, C.c_int, C.POINTER(_p)]),
     "oth_net_destroy": (C.c_int, [_p]),
     "oth_net_param_count": (_i64, [_p]),

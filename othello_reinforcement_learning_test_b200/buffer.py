@@ -1,0 +1,152 @@
+"""ReplayBuffer with the reference's interface, resident in HBM.
+
+Mirrors `src/train/buffer.py:15-123`: `ReplayBuffer(max_size)`, `add(data)`, `add_single`,
+`sample(batch_size) -> (states f32[B,3,8,8], policies f32[B,65], values f32[B,1])`, `__len__`, `clear`,
+`is_ready`, `get_statistics`.  Samples are kept packed (168 B: three bit-planes, 65 visit counts, label) in
+a device ring; `sample` draws indices with `random.sample` -- exactly what the reference does, so a seeded
+run returns the same minibatch -- and one kernel gathers + expands them.  `sample_torch` hands the trainer
+CUDA tensors without a host hop; `add_packed` / `add_from_worker` take the self-play engine's records as
+they are (host array or straight from device memory).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import random
+from typing import List, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import MEM_DEVICE, MEM_HOST, Context, check, ptr
+
+
+def pack_training_data(data) -> np.ndarray:
+    """[(state f32[3,8,8], policy f32[65], value)] -> packed oth_sample records.
+
+    The planes are 0/1 by construction (get_tensor_input).  Policies are stored as 16-bit counts: a visit
+    distribution n_i / N is recovered exactly when N <= 65535 (counts = round(p * N) with N inferred as the
+    smallest total that makes every entry integral); arbitrary float policies are quantised to 1/65535."""
+    n = len(data)
+    out = np.zeros(n, _lib.SAMPLE_DTYPE)
+    if n == 0:
+        return out
+    w = (1 << np.arange(64, dtype=np.uint64))
+    states = np.stack([d[0] for d in data]).reshape(n, 3, 64)
+    for k, name in enumerate(("self_b", "opp_b", "legal")):
+        out[name] = ((states[:, k] > 0.5).astype(np.uint64) * w).sum(axis=1, dtype=np.uint64)
+    pol = np.stack([np.asarray(d[1], np.float64) for d in data])                 # [n,65]
+    counts = np.rint(pol * 65535.0)                                                # fallback: 1/65535 quantisation
+    todo = np.ones(n, bool)
+    for total in range(1, 1025):                                                   # smallest N with p*N integral
+        if not todo.any():
+            break
+        c = pol[todo] * total
+        r = np.rint(c)
+        good = (np.abs(c - r).max(axis=1) < 2e-3) & (r.sum(axis=1) == total)
+        if good.any():
+            idx = np.flatnonzero(todo)[good]
+            counts[idx] = r[good]
+            todo[idx] = False
+    out["visits"] = counts.astype(np.uint16)
+    out["n_children"] = (counts > 0).sum(axis=1).astype(np.uint8)
+    out["value"] = np.rint([float(d[2]) for d in data]).astype(np.int8)
+    out["game"] = -1
+    return out
+
+
+class ReplayBuffer:
+    """Drop-in for `src.train.buffer.ReplayBuffer` (buffer.py:15-123), device-resident."""
+
+    def __init__(self, max_size: int = 100000, ctx: Context | None = None):
+        self.max_size = int(max_size)
+        self.ctx = ctx or Context.default()
+        h = C.c_void_p()
+        check(self.ctx.lib.oth_replay_create(self.ctx.handle, self.max_size, C.byref(h)))
+        self.handle = h
+
+    # ---- filling ----------------------------------------------------------------------------------
+    def add(self, data: List[Tuple[np.ndarray, np.ndarray, float]]) -> None:
+        """buffer.py:33-45"""
+        self.add_packed(pack_training_data(list(data)))
+
+    def add_single(self, state: np.ndarray, policy: np.ndarray, value: float) -> None:
+        """buffer.py:47-56"""
+        self.add([(state, policy, value)])
+
+    def add_packed(self, samples: np.ndarray) -> None:
+        assert samples.dtype == _lib.SAMPLE_DTYPE
+        samples = np.ascontiguousarray(samples)
+        check(self.ctx.lib.oth_replay_add(self.handle, ptr(samples), samples.size, MEM_HOST))
+
+    def add_from_worker(self, worker) -> int:
+        """Append the last campaign of a ParallelSelfPlayWorker device-to-device (no host hop)."""
+        dev_ptr, n = worker._engine.samples_device()
+        if n:
+            check(self.ctx.lib.oth_replay_add(self.handle, dev_ptr, n, MEM_DEVICE))
+        return n
+
+    # ---- sampling ---------------------------------------------------------------------------------
+    def _draw(self, batch_size: int) -> np.ndarray:
+        n = len(self)
+        if n < batch_size:
+            raise ValueError(f"Buffer size ({n}) is smaller than batch size ({batch_size})")    # buffer.py:71-74
+        return np.asarray(random.sample(range(n), batch_size), np.int64)                        # buffer.py:78
+
+    def sample(self, batch_size: int):
+        """buffer.py:58-84 -> numpy (states [B,3,8,8], policies [B,65], values [B,1])"""
+        idx = self._draw(batch_size)
+        st = np.empty((batch_size, 3, 8, 8), np.float32); po = np.empty((batch_size, 65), np.float32)
+        va = np.empty((batch_size, 1), np.float32)
+        check(self.ctx.lib.oth_replay_gather(self.handle, ptr(idx), batch_size, ptr(st), ptr(po), ptr(va), MEM_HOST))
+        return st, po, va
+
+    def sample_torch(self, batch_size: int, device=None):
+        """Same minibatch as CUDA tensors, written by the gather kernel (for trainer.py:264-269)."""
+        import torch
+        dev = torch.device(device) if device is not None else torch.device("cuda", self.ctx.device)
+        idx = torch.from_numpy(self._draw(batch_size)).to(dev)
+        st = torch.empty((batch_size, 3, 8, 8), dtype=torch.float32, device=dev)
+        po = torch.empty((batch_size, 65), dtype=torch.float32, device=dev)
+        va = torch.empty((batch_size, 1), dtype=torch.float32, device=dev)
+        torch.cuda.current_stream(dev).synchronize()
+        check(self.ctx.lib.oth_replay_gather(self.handle, ptr(idx), batch_size, ptr(st), ptr(po), ptr(va), MEM_DEVICE))
+        self.ctx.sync()
+        return st, po, va
+
+    # ---- bookkeeping --------------------------------------------------------------------------------
+    def __len__(self) -> int:
+        return int(self.ctx.lib.oth_replay_size(self.handle))
+
+    def clear(self) -> None:
+        check(self.ctx.lib.oth_replay_clear(self.handle))
+
+    def is_ready(self, min_size: int) -> bool:
+        return len(self) >= min_size
+
+    def get_statistics(self) -> dict:
+        """buffer.py:102-123"""
+        n = len(self)
+        if n == 0:
+            return {"size": 0, "max_size": self.max_size, "fill_rate": 0.0, "value_mean": 0.0, "value_std": 0.0}
+        m, s = C.c_double(0), C.c_double(0)
+        check(self.ctx.lib.oth_replay_value_stats(self.handle, C.byref(m), C.byref(s)))
+        return {"size": n, "max_size": self.max_size, "fill_rate": n / self.max_size, "value_mean": m.value, "value_std": s.value}
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.ctx.lib.oth_replay_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PrioritizedReplayBuffer(ReplayBuffer):
+    """buffer.py:126-177: the reference's class is a stub that samples uniformly; so does this one."""
+
+    def __init__(self, max_size: int = 100000, alpha: float = 0.6, ctx: Context | None = None):
+        super().__init__(max_size, ctx)
+        self.alpha = alpha

@@ -71,6 +71,45 @@ __global__ void __launch_bounds__(kBlock) k_tensor_input(const uint64_t* __restr
     }
 }
 
+// ---- baseline players of the evaluation arena (src/eval/players.py) -------------------------------------
+// RandomPlayer.get_action (players.py:60-67): uniform over get_legal_moves() (64 when the side must pass).
+__global__ void __launch_bounds__(kBlock) k_choose_random(const uint64_t* __restrict__ me, const uint64_t* __restrict__ you,
+                                                          const uint64_t* __restrict__ salt, uint64_t seed,
+                                                          int32_t* __restrict__ action, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t lg = legal_moves(me[i], you[i]);
+        if (lg == 0) { action[i] = kPass; continue; }
+        const uint64_t r = mix64(seed ^ mix64(salt ? salt[i] : (uint64_t)i));
+        action[i] = nth_set_bit(lg, (int)(((r >> 32) * (uint64_t)popc64(lg)) >> 32));
+    }
+}
+
+// GreedyPlayer.get_action (players.py:79-113), including its scoring rule as written: after the trial move the
+// board is seen from the other side; on even move counts the score is the mover's discs (get_stone_counts()[1]),
+// on odd move counts it is get_stone_counts()[0] -- the OPPONENT's discs.  First maximum in ascending order.
+__global__ void __launch_bounds__(kBlock) k_choose_greedy(const uint64_t* __restrict__ me, const uint64_t* __restrict__ you,
+                                                          const int32_t* __restrict__ move_count,
+                                                          int32_t* __restrict__ action, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t a = me[i], b = you[i];
+        uint64_t lg = legal_moves(a, b);
+        if (lg == 0) { action[i] = kPass; continue; }
+        const bool even = (move_count[i] & 1) == 0;
+        int best = -1, best_score = -1;
+        while (lg) {
+            const int sq = ctz64(lg);
+            lg &= lg - 1;
+            uint64_t x = a, y = b;
+            apply_known_legal(x, y, sq);                 // x = new side to move, y = the mover
+            const int score = even ? popc64(y) : popc64(x);
+            if (score > best_score) { best_score = score; best = sq; }
+        }
+        action[i] = best;
+    }
+}
+
 // ---- random playouts ---------------------------------------------------------------
 // One game per thread, state in registers from reset to the terminal position; the only
 // global traffic is the optional 20 B/game result record.  Warp ballots decide whether
@@ -297,6 +336,38 @@ int oth_tensor_input(oth_ctx* ctx, const uint64_t* self_b, const uint64_t* opp_b
     if (st.failed) return OTH_ERR_CUDA;
     OTH_REQUIRE(((uintptr_t)o & 15) == 0, OTH_ERR_ARG, "oth_tensor_input: output must be 16-byte aligned");
     k_tensor_input<<<grid_for(n * 48, kBlock, ctx->sm_count), kBlock, 0, ctx->stream>>>(a, b, (float4*)o, n);
+    LAUNCH_CHECK(ctx);
+    return st.finish();
+}
+
+int oth_choose_random(oth_ctx* ctx, const uint64_t* self_b, const uint64_t* opp_b, const uint64_t* salt, uint64_t seed,
+                      int32_t* action_out, int64_t n, int mem)
+{
+    OTH_REQUIRE(ctx && (n == 0 || (self_b && opp_b && action_out)), OTH_ERR_ARG, "oth_choose_random: NULL argument");
+    OTH_REQUIRE(n >= 0, OTH_ERR_ARG, "oth_choose_random: n < 0");
+    if (n == 0) return OTH_OK;
+    OTH_CHECK_CUDA(cudaSetDevice(ctx->device));
+    Staged st(ctx, mem);
+    const uint64_t* a = st.in(self_b, n); const uint64_t* b = st.in(opp_b, n); const uint64_t* sl = st.in(salt, n);
+    int32_t* act = st.out(action_out, n);
+    if (st.failed) return OTH_ERR_CUDA;
+    k_choose_random<<<grid_for(n, kBlock, ctx->sm_count), kBlock, 0, ctx->stream>>>(a, b, sl, seed, act, n);
+    LAUNCH_CHECK(ctx);
+    return st.finish();
+}
+
+int oth_choose_greedy(oth_ctx* ctx, const uint64_t* self_b, const uint64_t* opp_b, const int32_t* move_count,
+                      int32_t* action_out, int64_t n, int mem)
+{
+    OTH_REQUIRE(ctx && (n == 0 || (self_b && opp_b && move_count && action_out)), OTH_ERR_ARG, "oth_choose_greedy: NULL argument");
+    OTH_REQUIRE(n >= 0, OTH_ERR_ARG, "oth_choose_greedy: n < 0");
+    if (n == 0) return OTH_OK;
+    OTH_CHECK_CUDA(cudaSetDevice(ctx->device));
+    Staged st(ctx, mem);
+    const uint64_t* a = st.in(self_b, n); const uint64_t* b = st.in(opp_b, n); const int32_t* mc = st.in(move_count, n);
+    int32_t* act = st.out(action_out, n);
+    if (st.failed) return OTH_ERR_CUDA;
+    k_choose_greedy<<<grid_for(n, kBlock, ctx->sm_count), kBlock, 0, ctx->stream>>>(a, b, mc, act, n);
     LAUNCH_CHECK(ctx);
     return st.finish();
 }

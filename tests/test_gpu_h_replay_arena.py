@@ -1,0 +1,111 @@
+"""GPU parity for the rows SURVEY.md 8(f) marks "next": device-resident replay buffer and batched arena,
+against fixtures produced by the reference's own ReplayBuffer / Arena (oracle/gen_golden.py)."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import cref
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_replay_buffer_minibatches_equal_the_reference(golden_games):
+    import torch
+    import othello_reinforcement_learning_test_b200 as pkg
+    from oracle.gen_golden import replay_fixture_data
+    g = dict(np.load(os.path.join(GOLDEN, "replay_ref.npz")))
+    data = replay_fixture_data(golden_games)
+    buf = pkg.ReplayBuffer(max_size=500)
+    assert len(buf) == 0 and not buf.is_ready(1) and buf.get_statistics()["size"] == 0
+    with pytest.raises(ValueError):
+        buf.sample(1)                                            # buffer.py:71-74
+    buf.add(data[:300]); buf.add(data[300:])                     # 700 samples into 500 slots: the oldest 200 fall out
+    assert len(buf) == 500 and buf.is_ready(500)
+    random.seed(5)
+    st, po, va = buf.sample(48)                                  # random.sample, like buffer.py:78
+    assert st.shape == (48, 3, 8, 8) and po.shape == (48, 65) and va.shape == (48, 1)
+    assert np.array_equal(st, g["states"]) and np.array_equal(po, g["policies"]) and np.array_equal(va, g["values"])
+    random.seed(6)
+    st2, po2, va2 = buf.sample(500)
+    assert np.array_equal(st2.sum(axis=0), g["all_states_sum"]) and np.array_equal(po2, g["all_policies"])
+    assert np.array_equal(va2, g["all_values"])
+    s = buf.get_statistics()
+    assert [s["size"], s["max_size"], s["fill_rate"]] == g["stats"][:3].tolist()
+    assert abs(s["value_mean"] - g["stats"][3]) < 1e-12 and abs(s["value_std"] - g["stats"][4]) < 1e-12
+    random.seed(5)
+    ts, tp, tv = buf.sample_torch(48)                            # same minibatch, straight into CUDA tensors
+    assert ts.is_cuda and np.array_equal(ts.cpu().numpy(), g["states"]) and np.array_equal(tp.cpu().numpy(), g["policies"])
+    assert np.array_equal(tv.cpu().numpy(), g["values"])
+    buf.clear()
+    assert len(buf) == 0
+    buf.add_single(*data[0])
+    assert len(buf) == 1 and np.array_equal(buf.sample(1)[1][0], data[0][1])
+
+
+def test_replay_buffer_takes_a_campaign_device_to_device():
+    import othello_reinforcement_learning_test_b200 as pkg
+    from othello_reinforcement_learning_test_b200.self_play import samples_to_training_data
+    w = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", num_simulations=10, temperature_threshold=15,
+                                   num_parallel_games=8, seed=4, verbose=False)
+    packed = w.execute_episodes_packed(16)
+    buf = pkg.ReplayBuffer(max_size=10000)
+    n = buf.add_from_worker(w)
+    assert n == packed.size == len(buf)
+    random.seed(1)
+    idx = random.sample(range(n), 64)
+    random.seed(1)
+    st, po, va = buf.sample(64)
+    want = samples_to_training_data(packed)                     # sorted by (game, ply); the device order is flush order
+    by_key = {(int(p["game"]), int(p["ply"])): i for i, p in enumerate(packed[np.lexsort((packed["ply"], packed["game"]))])}
+    for k, i in enumerate(idx):
+        j = by_key[(int(packed[i]["game"]), int(packed[i]["ply"]))]
+        assert np.array_equal(st[k], want[j][0]) and np.array_equal(po[k], want[j][1]) and va[k, 0] == want[j][2]
+
+
+def test_batched_arena_equals_the_reference_arena():
+    import othello_reinforcement_learning_test_b200 as pkg
+    g = dict(np.load(os.path.join(GOLDEN, "arena_ref.npz")))
+
+    def pack(results):
+        return np.array([[r.winner, r.player1_score, r.player2_score, r.num_moves] for r in results], np.int32)
+    arena = pkg.BatchArena()
+    assert np.array_equal(pack(arena.play_matches(pkg.GreedyPlayer("A"), pkg.GreedyPlayer("B"), num_games=4)), g["greedy_vs_greedy"])
+    for sims in (8, 25):
+        mp = pkg.MCTSPlayer(None, "cuda", num_simulations=sims)              # model None = the integer test evaluator
+        assert np.array_equal(pack(arena.play_matches(mp, pkg.GreedyPlayer("G"), num_games=4)), g[f"mcts{sims}_vs_greedy"])
+        assert np.array_equal(pack(arena.play_matches(pkg.GreedyPlayer("G"), mp, num_games=2, alternate_colors=False)),
+                              g[f"greedy_vs_mcts{sims}"])
+    ev = pkg.evaluate_player(pkg.GreedyPlayer("A"), pkg.GreedyPlayer("B"), num_games=6)
+    assert [ev["win_rate"], ev["avg_score"], ev["avg_moves"]] == g["evaluate_greedy"].tolist()
+    assert str(ev["results"][0]).startswith(("A wins", "B wins", "Draw"))
+
+
+def test_greedy_and_random_choices_against_the_oracle(golden_games):
+    import othello_reinforcement_learning_test_b200 as pkg
+    live = np.flatnonzero(golden_games["terminal"] == 0)
+    S, O, MC = golden_games["self_b"][live], golden_games["opp_b"][live], golden_games["move_count"][live]
+    act = pkg.GreedyPlayer().get_actions(S, O, MC, np.arange(S.size))
+    rnd = pkg.RandomPlayer(seed=3).get_actions(S, O, MC, np.arange(S.size))
+    hist = {}
+    for i in range(0, S.size, 7):
+        s, o, mc = int(S[i]), int(O[i]), int(MC[i])
+        legal = cref.legal_list(s, o)
+        best, best_score = legal[0], -1                            # players.py:87-113 restated
+        if legal != [64]:
+            for a in legal:
+                ok, s2, o2, _ = cref.make_move(s, o, mc, a)
+                score = bin(o2).count("1") if mc % 2 == 0 else bin(s2).count("1")
+                if score > best_score:
+                    best, best_score = a, score
+        else:
+            best = 64
+        assert act[i] == best, i
+        assert int(rnd[i]) in legal
+        hist[len(legal)] = hist.get(len(legal), 0) + 1
+    # a whole match against the random player finishes, with plausible scores
+    res = pkg.BatchArena().play_matches(pkg.MCTSPlayer(None, "cuda", num_simulations=5), pkg.RandomPlayer(seed=9), num_games=32)
+    assert len(res) == 32 and all(r.player1_score + r.player2_score <= 64 and 9 <= r.num_moves <= 130 for r in res)
+    assert len({(r.player1_score, r.num_moves) for r in res}) > 8     # the random opponent really varies

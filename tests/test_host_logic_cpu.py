@@ -201,3 +201,16 @@ def test_multi_process_plumbing_gloo_world_size_2():
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_pack_training_data_round_trips_exactly(golden_games):
+    from oracle.gen_golden import replay_fixture_data
+    from othello_reinforcement_learning_test_b200.buffer import pack_training_data
+    from othello_reinforcement_learning_test_b200.self_play import planes_from_bits
+    data = replay_fixture_data(golden_games)[:200]
+    packed = pack_training_data(data)
+    st = planes_from_bits(packed["self_b"], packed["opp_b"], packed["legal"])
+    counts = packed["visits"].astype(np.float32)
+    pol = counts / counts.sum(axis=1, keepdims=True, dtype=np.float32)
+    for i, (s, p, v) in enumerate(data):
+        assert np.array_equal(st[i], s) and np.array_equal(pol[i], p) and float(packed["value"][i]) == v
