@@ -145,6 +145,11 @@ int oth_search_apply(oth_search* s, const float* probs, const float* value, int 
 /* MCTS.search / BatchMCTS.search_batch (mcts.py:49-98, parallel_self_play.py:80-170) fully on the
  * device with `net` (or the hash-net when OTH_FLAG_EVAL_HASHNET).  Call after oth_search_begin. */
 int oth_search_run(oth_search* s, oth_net* net, int num_simulations, int add_dirichlet_noise, uint64_t seed);
+/* Opt-in throughput mode (INFLIGHT_K): up to inflight_k simulations per game per network launch, kept apart by
+ * virtual loss; deterministic; inflight_k == 1 is identical to oth_search_run, larger values deviate from the
+ * reference's visit counts by construction (tests report the total-variation distance). */
+int oth_search_run_waves(oth_search* s, oth_net* net, int num_simulations, int inflight_k, int add_dirichlet_noise,
+                         uint64_t seed);
 /* root child statistics: visits int32 [n,65], q float64 [n,65] (0 for non-children),
  * n_evals int32 [n].  Any may be NULL. */
 int oth_search_results(oth_search* s, int32_t* visits, double* q, int32_t* n_evals, int mem);

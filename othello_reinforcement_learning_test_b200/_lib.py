@@ -86,6 +86,7 @@ _PROTOS = {
     "oth_search_collect": (C.c_int, [_p, _p, _p, _p, C.c_int]),
     "oth_search_apply": (C.c_int, [_p, _p, _p, C.c_int]),
     "oth_search_run": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_uint64]),
+    "oth_search_run_waves": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "oth_search_results": (C.c_int, [_p, _p, _p, _p, C.c_int]),
     "oth_search_policy": (C.c_int, [_p, C.c_double, _p, C.c_int]),
     "oth_search_stats": (C.c_int, [_p, C.POINTER(C.c_uint64)]),

@@ -55,8 +55,12 @@ class TreeSearch:
         assert probs.shape == (self.n, 65) and value.shape == (self.n,)
         check(self.ctx.lib.oth_search_apply(self.handle, ptr(probs), ptr(value), MEM_HOST))
 
-    def run(self, net_handle, sims: int, add_noise: bool, seed: int):
-        check(self.ctx.lib.oth_search_run(self.handle, net_handle, int(sims), int(bool(add_noise)), int(seed) & (2**64 - 1)))
+    def run(self, net_handle, sims: int, add_noise: bool, seed: int, inflight: int = 1):
+        if inflight > 1:
+            check(self.ctx.lib.oth_search_run_waves(self.handle, net_handle, int(sims), int(inflight), int(bool(add_noise)),
+                                                    int(seed) & (2**64 - 1)))
+        else:
+            check(self.ctx.lib.oth_search_run(self.handle, net_handle, int(sims), int(bool(add_noise)), int(seed) & (2**64 - 1)))
 
     def results(self):
         v = np.empty((self.n, 65), np.int32); q = np.empty((self.n, 65), np.float64); e = np.empty(self.n, np.int32)
@@ -97,7 +101,7 @@ class MCTS:
     def __init__(self, model, device, c_puct: float = 1.0, dirichlet_alpha: float = 0.3,
                  dirichlet_epsilon: float = 0.25, *, evaluator: str = "auto", root_n_sum: bool = False,
                  q_canonical: bool = False, engine: str | None = None, eval_cache: bool = False,
-                 ctx: Context | None = None):
+                 inflight: int = 1, ctx: Context | None = None):
         self.model = model
         self.device = device
         self.c_puct = c_puct
@@ -105,6 +109,7 @@ class MCTS:
         self.dirichlet_epsilon = dirichlet_epsilon
         self.root_n_sum, self.q_canonical = root_n_sum, q_canonical
         self.eval_cache = eval_cache          # position-keyed evaluation cache (native evaluator only; same results)
+        self.inflight = int(inflight)         # > 1: K simulations per game per launch with virtual loss (deviates from the reference)
         self._ctx = ctx
         self._engine = engine
         self._tree: TreeSearch | None = None
@@ -186,7 +191,7 @@ class MCTS:
                 t.apply(probs, val)
         else:
             net = self._native_net().handle if self.evaluator == "native" else None
-            t.run(net, num_simulations, add_noise, seed)
+            t.run(net, num_simulations, add_noise, seed, self.inflight)
         return t
 
     # -- the reference's public API ----------------------------------------------------------------

@@ -164,3 +164,33 @@ def test_canonical_flags_match_the_oracles_opt_in_mode(golden_games):
     # with the root's N in play the search spreads its visits (unlike REF mode)
     ref_mode, _, _ = pkg.MCTS(None, "cuda", c_puct=1.25).search_arrays(s, o, 40)
     assert (vis > 0).sum() > (ref_mode > 0).sum()
+
+
+def test_inflight_waves_k1_is_exact_and_larger_k_is_close(golden_games):
+    """Opt-in throughput mode: K simulations per game per launch with virtual loss.
+    K = 1 must reproduce the reference exactly; K > 1 deviates by construction -- report how much."""
+    import othello_reinforcement_learning_test_b200 as pkg
+    s, o = _positions(golden_games, 300, 77)
+    want, want_ev = cref.mcts_search_hashnet_batch(s, o, 50, 1.0)
+    v1, _, e1 = pkg.MCTS(None, "cuda", c_puct=1.0, inflight=1).search_arrays(s, o, 50)
+    assert np.array_equal(v1, want)
+    # the wave machinery itself with K = 1 (goes through oth_search_run_waves)
+    from othello_reinforcement_learning_test_b200.mcts import TreeSearch
+    ctx = pkg.Context.default(0)
+    t = TreeSearch(ctx, 300, 50); t.configure(1.0, 0.3, 0.25, pkg._lib.FLAG_EVAL_HASHNET); t.begin(s.copy(), o.copy())
+    pkg._lib.check(ctx.lib.oth_search_run_waves(t.handle, None, 50, 1, 0, 0))
+    vw, _, ew = t.results()
+    assert np.array_equal(vw, want) and np.array_equal(ew, want_ev)
+    tvs = {}
+    for K in (4, 8, 16):
+        vk, _, _ = pkg.MCTS(None, "cuda", c_puct=1.0, inflight=K).search_arrays(s, o, 50)
+        assert (vk.sum(axis=1) == 50).all() and ((vk > 0) <= (want >= 0)).all()
+        legal = np.array([[a in cref.legal_list(int(x), int(y)) for a in range(65)] for x, y in zip(s, o)])
+        assert not (vk[~legal] > 0).any()
+        tvs[K] = float(0.5 * np.abs(vk / 50.0 - want / 50.0).sum(axis=1).mean())
+    print("mean total-variation distance to the K=1 visit distribution:", tvs)
+    assert tvs[4] <= tvs[16] + 0.05 and tvs[16] < 0.6
+    # deterministic
+    a, _, _ = pkg.MCTS(None, "cuda", inflight=8).search_arrays(s, o, 50)
+    b, _, _ = pkg.MCTS(None, "cuda", inflight=8).search_arrays(s, o, 50)
+    assert np.array_equal(a, b)
