@@ -4,7 +4,7 @@
 // The reference runs one simulation at a time (src/mcts/mcts.py:89-92); that is the default everywhere in
 // this library and the mode every parity claim is made in.  With few games (an arena match, the GUI) one leaf
 // per game per network launch wastes the GPU, so this file adds waves: the K descents of a game are made one
-// after the other by the game's warp, each leaving a virtual visit (N += 1, W -/+= 1) on its path so that the
+// after the other by the game's warp, each leaving a virtual visit (a per-edge counter scored as a lost result) on its path so that the
 // next descent is pushed elsewhere; the K leaves are evaluated in ONE network launch; expansion and backup then
 // replace the virtual loss by the real value, again in descent order.  Everything a game does is sequential
 // inside its warp, so results are deterministic and the tree needs no atomics; K = 1 reproduces the reference
