@@ -187,13 +187,13 @@ def run_b200(args):
     net = worker.batch_mcts._native_net()
     engine = worker._get_engine(G, True)
 
-    cache_stats = np.zeros(4, np.int64)
+    cache_stats = np.zeros(5, np.int64)
 
     def device_step():
         import ctypes as C
         ns, ne = C.c_int64(0), C.c_int64(0)
         pkg._lib.check(ctx.lib.oth_selfplay_run(engine.handle, net.handle, G, C.byref(ns), C.byref(ne)))
-        st = (C.c_uint64 * 4)()
+        st = (C.c_uint64 * 5)()
         pkg._lib.check(ctx.lib.oth_selfplay_stats(engine.handle, st))
         cache_stats[:] += np.array(list(st), np.int64)
         return int(ns.value), int(ne.value)
@@ -304,7 +304,8 @@ def run_b200(args):
             "expansions_per_game": float(tot[1].item()) / games_total, "samples_per_game": float(tot[0].item()) / games_total,
             "eval_cache": {"enabled": not args.no_eval_cache, "rank0_expansions": int(evals), "rank0_network_positions": int(cache_stats[0]),
                            "rank0_cache_hits": int(cache_stats[1]), "rank0_same_step_duplicates": int(cache_stats[2]),
-                           "rank0_hash_collisions": int(cache_stats[3]),
+                           "rank0_hash_collisions": int(cache_stats[3]), "rank0_searches_run": int(cache_stats[4]),
+                           "rank0_searches_requested": int(samples),
                            "note": "result-transparent: cached / shared outputs are bit-identical to re-evaluation; cache is emptied at the start of every campaign"},
             "wall_s_timed_region": wall_s,
             "random_playout": {"games_per_s": n_po / (po_ms / 1000.0), "games": n_po,

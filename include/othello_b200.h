@@ -126,6 +126,10 @@ int oth_net_forward(oth_net* net, const uint64_t* self_b, const uint64_t* opp_b,
 #define OTH_FLAG_Q_CANONICAL 2u  /* negate child Q in select; default: un-negated (node.py:113,119) */
 #define OTH_FLAG_WINNER_BLACK 4u /* self-play labels from black's view; default: parallel_self_play.py:397-404 */
 #define OTH_FLAG_EVAL_HASHNET 8u /* built-in integer test evaluator instead of the network */
+#define OTH_FLAG_NO_SEARCH_SHARING 32u /* self-play: do NOT let slots with identical root positions share one search
+                                          (sharing is result-transparent: the search is a deterministic function of the
+                                          root position; it is switched off by itself when per-game Dirichlet noise
+                                          enters the search, i.e. add_dirichlet_noise with OTH_FLAG_ROOT_N_SUM) */
 #define OTH_FLAG_EVAL_CACHE 16u  /* position-keyed evaluation cache + same-step dedup in HBM (result-transparent:
                                     the network's output for a position does not depend on its batch slot) */
 
@@ -191,8 +195,9 @@ int oth_selfplay_destroy(oth_selfplay* sp);
  * n_samples_out / n_evals_out are HOST scalars. */
 int oth_selfplay_run(oth_selfplay* sp, oth_net* net, int64_t num_episodes, int64_t* n_samples_out,
                      int64_t* n_evals_out);
-/* evaluation statistics of the last run (HOST uint64[4]), as oth_search_stats */
-int oth_selfplay_stats(oth_selfplay* sp, uint64_t* out4);
+/* statistics of the last run (HOST uint64[5]): [0..3] as oth_search_stats, [4] = searches actually run (slots with
+ * identical root positions share one) */
+int oth_selfplay_stats(oth_selfplay* sp, uint64_t* out5);
 /* copy the samples of the last run into a caller buffer (HOST or DEVICE) */
 int oth_selfplay_fetch(oth_selfplay* sp, oth_sample* out, int64_t capacity, int mem);
 /* device pointer + count of the last run's samples (for NCCL all-gather without a host hop) */

@@ -33,7 +33,7 @@ k_tree_begin(TreeDev t, const uint64_t* __restrict__ self_b, const uint64_t* __r
     t.root_self[g] = live ? self_b[g] : 0ULL;
     t.root_opp[g] = live ? opp_b[g] : 0ULL;
     t.active[g] = live ? 1 : 0;
-    t.n_nodes[g] = 0; t.n_edges[g] = 0; t.n_evals[g] = 0; t.sims_done[g] = 0; t.path_len[g] = 0;
+    t.n_nodes[g] = 0; t.n_edges[g] = 0; t.n_evals[g] = 0; t.sims_done[g] = 0; t.path_len[g] = 0; t.root_count[g] = 0;
     t.pending[g] = 0; t.eval_slot[g] = -1;
     t.leaf_self[g] = 0ULL; t.leaf_opp[g] = 0ULL; t.leaf_legal[g] = 0ULL;
     if (g == 0) *t.batch_count = 0;
@@ -89,47 +89,45 @@ k_tree_select(TreeDev t, int64_t n, float c32, uint32_t flags, uint32_t epoch, u
     const int lane = threadIdx.x & 31;
     if (g >= n) return;
     if (!t.active[g]) { if (lane == 0) t.pending[g] = 0; return; }
-    const int32_t* node_first = t.node_first + g * t.node_cap;
-    const int32_t* node_count = t.node_count + g * t.node_cap;
-    int32_t* edge_n = t.edge_n + g * (int64_t)t.edge_cap;
-    double* edge_w = t.edge_w + g * (int64_t)t.edge_cap;
-    const float* edge_p = t.edge_p + g * (int64_t)t.edge_cap;
-    const int32_t* edge_child = t.edge_child + g * (int64_t)t.edge_cap;
-    const uint8_t* edge_action = t.edge_action + g * (int64_t)t.edge_cap;
+    Edge* E = t.edges + g * (int64_t)t.edge_cap;
     int32_t* path = t.path + g * t.path_cap;
 
     uint64_t me = t.root_self[g], you = t.root_opp[g];
-    int node = 0, depth = 0;
+    int first = 0, cnt = t.root_count[g], depth = 0;
     int parent_n = (flags & OTH_FLAG_ROOT_N_SUM) ? t.sims_done[g] : 0;   // mcts.py:152-172: the root is never updated
     for (;;) {
-        const int first = node_first[node], cnt = node_count[node];
         const double root_of_n = sqrt((double)parent_n);
         double best = -INFINITY;
-        int best_e = 0x7FFFFFFF;
+        int best_e = 0x7FFFFFFF, b_n = 0, b_first = kEdgeLeaf, b_cnt = 0, b_act = 0;
         for (int k = lane; k < cnt; k += 32) {
-            const int e = first + k;
-            const int nv = edge_n[e];
-            double q = nv ? edge_w[e] / (double)nv : 0.0;                // node.py:51-60
+            const Edge ed = E[first + k];                                   // one 24-byte record per child
+            double q = ed.n ? ed.w / (double)ed.n : 0.0;                    // node.py:51-60
             if (flags & OTH_FLAG_Q_CANONICAL) q = -q;
-            const float cp = __fmul_rn(c32, edge_p[e]);                   // float32 product (weak Python scalar)
-            const double u = __ddiv_rn(__dmul_rn((double)cp, root_of_n), (double)(1 + nv));
+            const float cp = __fmul_rn(c32, ed.p);                          // float32 product (weak Python scalar)
+            const double u = __ddiv_rn(__dmul_rn((double)cp, root_of_n), (double)(1 + ed.n));
             const double s = __dadd_rn(q, u);
-            if (s > best) { best = s; best_e = e; }                       // strict >: first maximum wins
+            if (s > best) {                                                 // strict >: first maximum wins
+                best = s; best_e = first + k; b_n = ed.n; b_first = ed.child_first; b_cnt = ed.child_count; b_act = ed.action;
+            }
         }
+        int win_lane = lane;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double os = __shfl_xor_sync(kFull, best, o);
             const int oe = __shfl_xor_sync(kFull, best_e, o);
-            if (os > best || (os == best && oe < best_e)) { best = os; best_e = oe; }
+            const int ol = __shfl_xor_sync(kFull, win_lane, o);
+            if (os > best || (os == best && oe < best_e)) { best = os; best_e = oe; win_lane = ol; }
         }
         const int e = best_e;
-        parent_n = edge_n[e];
+        parent_n = __shfl_sync(kFull, b_n, win_lane);
+        const int child_first = __shfl_sync(kFull, b_first, win_lane);
+        cnt = __shfl_sync(kFull, b_cnt, win_lane);
+        const int action = __shfl_sync(kFull, b_act, win_lane);
         if (lane == 0) path[depth] = e;
         ++depth;
-        apply_known_legal(me, you, (int)edge_action[e]);                  // mcts.py:122
-        const int child = edge_child[e];
-        if (child < 0 || depth >= t.path_cap) break;
-        node = child;
+        apply_known_legal(me, you, action);                                 // mcts.py:122
+        if (cnt == 0 || depth >= t.path_cap) break;                         // child not expanded: this is the leaf
+        first = child_first;
     }
     const uint64_t lg = legal_moves(me, you);
     const bool terminal = lg == 0 && legal_moves(you, me) == 0;           // mcts.py:127
@@ -137,9 +135,9 @@ k_tree_select(TreeDev t, int64_t n, float c32, uint32_t flags, uint32_t epoch, u
         if (terminal) {
             double v = (double)winner(me, you);                            // mcts.py:129-130
             for (int i = depth - 1; i >= 0; --i) {                         // mcts.py:152-168
-                const int e = path[i];
-                edge_n[e] += 1;
-                edge_w[e] += v;
+                Edge* ed = E + path[i];
+                ed->n += 1;
+                ed->w += v;
                 v = -v;
             }
             t.sims_done[g] += 1;
@@ -198,37 +196,35 @@ k_tree_expand(TreeDev t, int64_t n, const float* __restrict__ policy, const floa
     if (policy_is_raw && lane == 0) mask_and_renormalise(pri, lg);        // node.py:71-80
     __syncwarp();
     const int depth = t.path_len[g];
-    const int node_idx = depth == 0 ? 0 : t.n_nodes[g];
     const int cnt = lg ? popc64(lg) : 1;                                   // [64] = forced pass (bitboard.pyx:176-178)
     const int first = t.n_edges[g];
-    if (node_idx >= t.node_cap || first + cnt > t.edge_cap) {
+    if (first + cnt > t.edge_cap) {
         if (lane == 0) { atomicExch(t.error_flag, 1); t.pending[g] = 0; }
         return;
     }
-    int32_t* edge_n = t.edge_n + g * (int64_t)t.edge_cap;
-    double* edge_w = t.edge_w + g * (int64_t)t.edge_cap;
-    float* edge_p = t.edge_p + g * (int64_t)t.edge_cap;
-    int32_t* edge_child = t.edge_child + g * (int64_t)t.edge_cap;
-    uint8_t* edge_action = t.edge_action + g * (int64_t)t.edge_cap;
+    Edge* E = t.edges + g * (int64_t)t.edge_cap;
     for (int k = lane; k < cnt; k += 32) {
+        Edge ed;
+        ed.w = 0.0; ed.n = 0; ed.child_first = kEdgeLeaf; ed.child_count = 0; ed.pad = 0;
         const int action = lg ? nth_set_bit(lg, k) : kPass;
-        const int e = first + k;
-        edge_n[e] = 0; edge_w[e] = 0.0; edge_p[e] = pri[action]; edge_child[e] = -1; edge_action[e] = (uint8_t)action;
+        ed.p = pri[action]; ed.action = (uint8_t)action;
+        E[first + k] = ed;
     }
     if (lane == 0) {
-        t.node_first[g * t.node_cap + node_idx] = first;
-        t.node_count[g * t.node_cap + node_idx] = cnt;
-        t.n_nodes[g] = node_idx + 1;
+        t.n_nodes[g] += 1;
         t.n_edges[g] = first + cnt;
         t.n_evals[g] += 1;
-        if (depth > 0) {
+        if (depth == 0) {
+            t.root_count[g] = cnt;                                         // the root's children are edges [0, cnt)
+        } else {
             const int32_t* path = t.path + g * t.path_cap;
-            edge_child[path[depth - 1]] = node_idx;
+            Edge* leaf = E + path[depth - 1];
+            leaf->child_first = first; leaf->child_count = (uint8_t)cnt;
             double v = (double)leaf_value;                                 // value.item(), mcts.py:144
             for (int i = depth - 1; i >= 0; --i) {
-                const int e = path[i];
-                edge_n[e] += 1;
-                edge_w[e] += v;
+                Edge* ed = E + path[i];
+                ed->n += 1;
+                ed->w += v;
                 v = -v;
             }
             t.sims_done[g] += 1;
@@ -299,15 +295,15 @@ __global__ void __launch_bounds__(kSearchBlock)
 k_root_noise(TreeDev t, int64_t n, double alpha, double eps, uint64_t seed, const int32_t* __restrict__ salt)
 {
     const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (g >= n || !t.active[g] || t.n_nodes[g] < 1) return;
-    float* edge_p = t.edge_p + g * (int64_t)t.edge_cap;
-    const int first = t.node_first[g * t.node_cap], cnt = t.node_count[g * t.node_cap];
+    if (g >= n || !t.active[g] || t.root_count[g] < 1) return;
+    Edge* E = t.edges + g * (int64_t)t.edge_cap;
+    const int cnt = t.root_count[g];
     uint64_t s = mix64(seed ^ mix64((uint64_t)g * 0x9E3779B97F4A7C15ULL + (salt ? (uint64_t)salt[g] : 0ULL)));
     double noise[64];
     double total = 0.0;
     for (int k = 0; k < cnt && k < 64; ++k) { noise[k] = gamma_sample(alpha, s); total += noise[k]; }
     for (int k = 0; k < cnt && k < 64; ++k)
-        edge_p[first + k] = (float)((1.0 - eps) * (double)edge_p[first + k] + eps * (noise[k] / total));
+        E[k].p = (float)((1.0 - eps) * (double)E[k].p + eps * (noise[k] / total));
 }
 
 __global__ void __launch_bounds__(kSearchBlock)
@@ -322,13 +318,13 @@ k_tree_results(TreeDev t, int64_t n, int32_t* __restrict__ visits, double* __res
     }
     __syncwarp();
     if (lane == 0 && n_evals) n_evals[g] = t.n_evals[g];
-    if (!t.active[g] || t.n_nodes[g] < 1) return;
-    const int first = t.node_first[g * t.node_cap], cnt = t.node_count[g * t.node_cap];
+    if (!t.active[g] || t.root_count[g] < 1) return;
+    const Edge* E = t.edges + g * (int64_t)t.edge_cap;
+    const int cnt = t.root_count[g];
     for (int k = lane; k < cnt; k += 32) {
-        const int64_t e = g * (int64_t)t.edge_cap + first + k;
-        const int a = t.edge_action[e], nv = t.edge_n[e];
-        if (visits) visits[g * 65 + a] = nv;
-        if (q) q[g * 65 + a] = nv ? t.edge_w[e] / (double)nv : 0.0;
+        const Edge ed = E[k];
+        if (visits) visits[g * 65 + ed.action] = ed.n;
+        if (q) q[g * 65 + ed.action] = ed.n ? ed.w / (double)ed.n : 0.0;
     }
 }
 
@@ -339,13 +335,13 @@ __global__ void __launch_bounds__(kSearchBlock) k_tree_policy(TreeDev t, int64_t
     if (g >= n) return;
     float* p = out + g * 65;
     for (int j = 0; j < 65; ++j) p[j] = 0.f;
-    if (!t.active[g] || t.n_nodes[g] < 1) return;
-    const int first = t.node_first[g * t.node_cap], cnt = t.node_count[g * t.node_cap];
-    const int64_t base = g * (int64_t)t.edge_cap + first;
+    if (!t.active[g] || t.root_count[g] < 1) return;
+    const Edge* E = t.edges + g * (int64_t)t.edge_cap;
+    const int cnt = t.root_count[g];
     if (temperature == 0.0) {
         int best = 0;                                    // np.argmax: first maximum (node.py:171-174)
-        for (int k = 1; k < cnt; ++k) if (t.edge_n[base + k] > t.edge_n[base + best]) best = k;
-        p[t.edge_action[base + best]] = 1.0f;
+        for (int k = 1; k < cnt; ++k) if (E[k].n > E[best].n) best = k;
+        p[E[best].action] = 1.0f;
         return;
     }
     // counts ** (1/T) / sum, float32 (node.py:177-180).  For T == 1 the counts are small integers,
@@ -353,12 +349,12 @@ __global__ void __launch_bounds__(kSearchBlock) k_tree_policy(TreeDev t, int64_t
     const float ex = (float)(1.0 / temperature);
     float total = 0.f;
     for (int k = 0; k < cnt; ++k) {
-        const float c = (float)t.edge_n[base + k];
+        const float c = (float)E[k].n;
         total += (temperature == 1.0) ? c : powf(c, ex);
     }
     for (int k = 0; k < cnt; ++k) {
-        const float c = (float)t.edge_n[base + k];
-        p[t.edge_action[base + k]] = __fdiv_rn((temperature == 1.0) ? c : powf(c, ex), total);
+        const float c = (float)E[k].n;
+        p[E[k].action] = __fdiv_rn((temperature == 1.0) ? c : powf(c, ex), total);
     }
 }
 
@@ -393,9 +389,7 @@ int SearchHost::allocate(oth_ctx* c, int64_t games, int sims)
     A(t.leaf_self, G); A(t.leaf_opp, G); A(t.leaf_legal, G);
     A(t.batch_self, G); A(t.batch_opp, G); A(t.eval_slot, G); A(t.batch_count, 1);
     A(t.path, G * t.path_cap);
-    A(t.node_first, G * t.node_cap); A(t.node_count, G * t.node_cap);
-    A(t.edge_n, G * t.edge_cap); A(t.edge_w, G * t.edge_cap); A(t.edge_p, G * t.edge_cap);
-    A(t.edge_child, G * t.edge_cap); A(t.edge_action, G * t.edge_cap);
+    A(t.root_count, G); A(t.edges, G * t.edge_cap);
     A(t.eval_policy, G * 65); A(t.eval_value, G);
     A(t.error_flag, 1);
     A(t.leaf_h, G); A(t.leaf_src, G); A(t.dedup_of, G); A(t.stats, 4);
@@ -554,7 +548,7 @@ int SearchHost::check_overflow()
     int32_t flag = 0;
     OTH_CHECK_CUDA(cudaMemcpyAsync(&flag, t.error_flag, sizeof flag, cudaMemcpyDeviceToHost, ctx->stream));
     OTH_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-    OTH_REQUIRE(flag == 0, OTH_ERR_CAPACITY, "search: a tree pool overflowed (node_cap %d, edge_cap %d per game)", t.node_cap, t.edge_cap);
+    OTH_REQUIRE(flag == 0, OTH_ERR_CAPACITY, "search: a tree pool overflowed (edge_cap %d per game)", t.edge_cap);
     return OTH_OK;
 }
 

@@ -7,10 +7,23 @@ namespace oth {
 
 constexpr int kEdgesPerNodeBudget = 40;   // pool sizing only; a node may have up to 64 children
 
-// All arrays are device memory.  Per game g: nodes [g*node_cap .. +node_cap), edges
-// [g*edge_cap .. +edge_cap) allocated CSR-style in expansion order (node 0 = root).
-// An "edge" carries what the reference keeps on the child MCTSNode (node.py:28-45):
-// prior P (float32), visit_count N, value_sum W (float64) and the link to its own children.
+// An "edge" carries what the reference keeps on the child MCTSNode (node.py:28-45): prior P (float32),
+// visit_count N, value_sum W (float64) -- plus where that child's own edges live, so a descent needs ONE
+// dependent load per level (the 24-byte records of a node's children are contiguous).
+struct __align__(8) Edge {
+    double w;             // value_sum
+    int32_t n;            // visit_count
+    float p;              // prior
+    int32_t child_first;  // first edge of the child node; kEdgeLeaf = not expanded, kEdgePending = being expanded (waves)
+    uint8_t child_count;  // number of edges of the child node (0 while not expanded)
+    uint8_t action;       // 0..63 square, 64 pass
+    uint16_t pad;
+};
+static_assert(sizeof(Edge) == 24, "Edge record layout");
+constexpr int32_t kEdgeLeaf = -1, kEdgePending = -2;
+
+// All arrays are device memory.  Per game g the edges [g*edge_cap .. +edge_cap) are allocated CSR-style in
+// expansion order; the root's children are edges [0, root_count).
 struct TreeDev {
     int64_t games;            // capacity (slots)
     int node_cap, edge_cap, path_cap;
@@ -38,15 +51,8 @@ struct TreeDev {
     int32_t* dedup_of;               // [games] game whose evaluation this leaf shares
     unsigned long long* stats;       // [0] network positions, [1] cache hits, [2] same-step duplicates, [3] hash collisions
     int32_t* path;            // [games][path_cap] edge indices of the pending simulation
-    // per node
-    int32_t* node_first;      // first edge
-    int32_t* node_count;      // number of edges (0 = not expanded)
-    // per edge
-    int32_t* edge_n;
-    double* edge_w;
-    float* edge_p;
-    int32_t* edge_child;      // node index, -1 while the child is a leaf
-    uint8_t* edge_action;
+    int32_t* root_count;      // [games] number of root children (0 = root not expanded yet)
+    Edge* edges;              // [games][edge_cap]
     // evaluator outputs for the batch
     float* eval_policy;       // [games][65]
     float* eval_value;        // [games]

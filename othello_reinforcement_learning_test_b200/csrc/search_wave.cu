@@ -19,7 +19,6 @@ namespace oth {
 
 constexpr int kWaveWarps = 8;
 constexpr int kWaveBlock = kWaveWarps * 32;
-constexpr int kChildPending = -2;     // edge_child marker: a leaf of the current wave will expand here
 
 struct WaveDev {
     int K;
@@ -35,32 +34,39 @@ struct WaveDev {
     int32_t* edge_vn;     // [G][edge_cap] virtual visits currently on each edge (kept apart from N/W so that K = 1 is exact)
 };
 
-__device__ __forceinline__ int wave_pick_child(const TreeDev& t, const WaveDev& w, int64_t g, int node, int parent_n, float c32,
-                                                uint32_t flags, int lane)
+// One level of the descent: returns the chosen edge index and hands back what the next level needs.
+__device__ __forceinline__ int wave_pick_child(const TreeDev& t, const WaveDev& w, int64_t g, int first, int cnt, int parent_n,
+                                                float c32, uint32_t flags, int lane, int& n_eff, int& child_first, int& child_cnt,
+                                                int& action)
 {
-    const int first = t.node_first[g * t.node_cap + node], cnt = t.node_count[g * t.node_cap + node];
     const int64_t eb = g * (int64_t)t.edge_cap;
     const double root_of_n = sqrt((double)parent_n);
     double best = -INFINITY;
-    int best_e = 0x7FFFFFFF;
+    int best_e = 0x7FFFFFFF, b_n = 0, b_first = kEdgeLeaf, b_cnt = 0, b_act = 0;
     for (int k = lane; k < cnt; k += 32) {
-        const int e = first + k;
-        const int vn = w.edge_vn[eb + e];
-        const int nv = t.edge_n[eb + e] + vn;                                   // real + virtual visits
+        const Edge ed = t.edges[eb + first + k];
+        const int vn = w.edge_vn[eb + first + k];
+        const int nv = ed.n + vn;                                               // real + virtual visits
         // a virtual visit counts as a result that makes the edge look worse to its parent
-        const double wsum = vn ? t.edge_w[eb + e] + ((flags & OTH_FLAG_Q_CANONICAL) ? 1.0 : -1.0) * (double)vn : t.edge_w[eb + e];
+        const double wsum = vn ? ed.w + ((flags & OTH_FLAG_Q_CANONICAL) ? 1.0 : -1.0) * (double)vn : ed.w;
         double q = nv ? wsum / (double)nv : 0.0;
         if (flags & OTH_FLAG_Q_CANONICAL) q = -q;
-        const float cp = __fmul_rn(c32, t.edge_p[eb + e]);
+        const float cp = __fmul_rn(c32, ed.p);
         const double s = __dadd_rn(q, __ddiv_rn(__dmul_rn((double)cp, root_of_n), (double)(1 + nv)));
-        if (s > best) { best = s; best_e = e; }
+        if (s > best) { best = s; best_e = first + k; b_n = nv; b_first = ed.child_first; b_cnt = ed.child_count; b_act = ed.action; }
     }
+    int win_lane = lane;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double os = __shfl_xor_sync(0xFFFFFFFFu, best, o);
         const int oe = __shfl_xor_sync(0xFFFFFFFFu, best_e, o);
-        if (os > best || (os == best && oe < best_e)) { best = os; best_e = oe; }
+        const int ol = __shfl_xor_sync(0xFFFFFFFFu, win_lane, o);
+        if (os > best || (os == best && oe < best_e)) { best = os; best_e = oe; win_lane = ol; }
     }
+    n_eff = __shfl_sync(0xFFFFFFFFu, b_n, win_lane);
+    child_first = __shfl_sync(0xFFFFFFFFu, b_first, win_lane);
+    child_cnt = __shfl_sync(0xFFFFFFFFu, b_cnt, win_lane);
+    action = __shfl_sync(0xFFFFFFFFu, b_act, win_lane);
     return best_e;
 }
 
@@ -72,6 +78,7 @@ k_wave_select(TreeDev t, WaveDev w, int64_t n, int sims_target, float c32, uint3
     const int lane = threadIdx.x & 31;
     if (g >= n || !t.active[g]) return;
     const int64_t eb = g * (int64_t)t.edge_cap;
+    Edge* E = t.edges + eb;
     for (int k = 0; k < w.K; ++k) {
         if (lane == 0) w.state[g * w.K + k] = 0;
     }
@@ -81,31 +88,31 @@ k_wave_select(TreeDev t, WaveDev w, int64_t n, int sims_target, float c32, uint3
         if (t.sims_done[g] + in_flight >= sims_target) break;
         int32_t* path = w.path + (g * w.K + k) * (int64_t)t.path_cap;
         uint64_t me = t.root_self[g], you = t.root_opp[g];
-        int node = 0, depth = 0;
+        int first = 0, cnt = t.root_count[g], depth = 0;
         int parent_n = (flags & OTH_FLAG_ROOT_N_SUM) ? t.sims_done[g] + in_flight : 0;
-        int child = -1;
+        int child_first = kEdgeLeaf;
         for (;;) {
-            const int e = wave_pick_child(t, w, g, node, parent_n, c32, flags, lane);
-            parent_n = t.edge_n[eb + e] + w.edge_vn[eb + e];
+            int n_eff, c_cnt, action;
+            const int e = wave_pick_child(t, w, g, first, cnt, parent_n, c32, flags, lane, n_eff, child_first, c_cnt, action);
+            parent_n = n_eff;
             if (lane == 0) path[depth] = e;
             ++depth;
-            apply_known_legal(me, you, (int)t.edge_action[eb + e]);
-            child = t.edge_child[eb + e];
-            if (child < 0 || depth >= t.path_cap) break;
-            node = child;
+            apply_known_legal(me, you, action);
+            if (c_cnt == 0 || depth >= t.path_cap) break;
+            first = child_first; cnt = c_cnt;
         }
         __syncwarp();
-        if (child == kChildPending) break;         // an earlier descent of this wave already owns this leaf: end the wave here
+        if (child_first == kEdgePending) break;    // an earlier descent of this wave already owns this leaf: end the wave here
         const uint64_t lg = legal_moves(me, you);
         const bool terminal = lg == 0 && legal_moves(you, me) == 0;
         if (lane == 0) {
             if (terminal) {                          // scored at once, like mcts.py:127-130,152-168
                 double v = (double)winner(me, you);
-                for (int i = depth - 1; i >= 0; --i) { const int e = path[i]; t.edge_n[eb + e] += 1; t.edge_w[eb + e] += v; v = -v; }
+                for (int i = depth - 1; i >= 0; --i) { Edge* ed = E + path[i]; ed->n += 1; ed->w += v; v = -v; }
                 t.sims_done[g] += 1;
             } else {
                 for (int i = 0; i < depth; ++i) w.edge_vn[eb + path[i]] += 1;                       // virtual loss
-                t.edge_child[eb + path[depth - 1]] = kChildPending;
+                E[path[depth - 1]].child_first = kEdgePending;
                 const int64_t j = g * w.K + k;
                 w.leaf_self[j] = me; w.leaf_opp[j] = you; w.leaf_legal[j] = lg;
                 w.path_len[j] = depth;
@@ -157,30 +164,31 @@ __global__ void __launch_bounds__(kWaveBlock) k_wave_expand(TreeDev t, WaveDev w
         __syncwarp();
         const int depth = w.path_len[j];
         const int32_t* path = w.path + j * (int64_t)t.path_cap;
-        const int node_idx = t.n_nodes[g];
         const int cnt = lg ? popc64(lg) : 1;
         const int first = t.n_edges[g];
-        if (node_idx >= t.node_cap || first + cnt > t.edge_cap) {
+        if (first + cnt > t.edge_cap) {
             if (lane == 0) atomicExch(t.error_flag, 1);
             return;
         }
+        Edge* E = t.edges + eb;
         for (int c = lane; c < cnt; c += 32) {
+            Edge ed;
+            ed.w = 0.0; ed.n = 0; ed.child_first = kEdgeLeaf; ed.child_count = 0; ed.pad = 0;
             const int action = lg ? nth_set_bit(lg, c) : kPass;
-            const int64_t e = eb + first + c;
-            t.edge_n[e] = 0; t.edge_w[e] = 0.0; t.edge_p[e] = pri[action]; t.edge_child[e] = -1; t.edge_action[e] = (uint8_t)action;
+            ed.p = pri[action]; ed.action = (uint8_t)action;
+            E[first + c] = ed;
         }
         __syncwarp();
         if (lane == 0) {
-            t.node_first[g * t.node_cap + node_idx] = first;
-            t.node_count[g * t.node_cap + node_idx] = cnt;
-            t.n_nodes[g] = node_idx + 1;
+            t.n_nodes[g] += 1;
             t.n_edges[g] = first + cnt;
             t.n_evals[g] += 1;
-            t.edge_child[eb + path[depth - 1]] = node_idx;
+            Edge* leaf = E + path[depth - 1];
+            leaf->child_first = first; leaf->child_count = (uint8_t)cnt;
             double v = (double)w.value[src];
             for (int i = depth - 1; i >= 0; --i) {                  // the virtual visit becomes a real one (mcts.py:152-168)
-                const int64_t e = eb + path[i];
-                w.edge_vn[e] -= 1; t.edge_n[e] += 1; t.edge_w[e] += v; v = -v;
+                Edge* ed = E + path[i];
+                w.edge_vn[eb + path[i]] -= 1; ed->n += 1; ed->w += v; v = -v;
             }
             t.sims_done[g] += 1;
             w.state[j] = 0;

@@ -25,7 +25,14 @@ struct SelfPlayDev {
     oth_sample* staging;            // [slots][kMaxPlies]
     oth_sample* out;
     int64_t out_cap;
-    unsigned long long* counters;   // 0 started, 1 finished, 2 samples, 3 plies, 4 evals, 5 overflow
+    unsigned long long* counters;   // 0 started, 1 finished, 2 samples, 3 plies, 4 evals, 5 overflow, 6 searches run
+    // search-level sharing: slots whose root position is identical run ONE search (the search is a deterministic
+    // function of the root position), the others read the leader's root statistics
+    int32_t* leader;                // [slots] slot whose tree holds this slot's search
+    uint8_t* search_active;         // [slots] 1 = this slot runs a search this ply
+    uint32_t* root_h;               // [slots] index into the election table
+    unsigned long long* r_owner;    // [r_mask+1] (~ply << 32 | slot), atomicMin elects the leader
+    uint64_t r_mask;
 };
 
 __global__ void k_sp_reset(SelfPlayDev d, int64_t num_episodes)
@@ -33,7 +40,7 @@ __global__ void k_sp_reset(SelfPlayDev d, int64_t num_episodes)
     const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s == 0) {
         d.counters[0] = (unsigned long long)(num_episodes < d.slots ? num_episodes : d.slots);
-        d.counters[1] = d.counters[2] = d.counters[3] = d.counters[4] = d.counters[5] = 0ULL;
+        d.counters[1] = d.counters[2] = d.counters[3] = d.counters[4] = d.counters[5] = d.counters[6] = 0ULL;
     }
     if (s >= d.slots) return;
     const bool live = s < num_episodes;
@@ -41,6 +48,33 @@ __global__ void k_sp_reset(SelfPlayDev d, int64_t num_episodes)
     d.move_count[s] = 0;
     d.game_id[s] = live ? (int32_t)s : -1;
     d.active[s] = live ? 1 : 0;
+}
+
+// Elect one slot per distinct root position (phase 1) and point everybody else at it (phase 2).
+__global__ void __launch_bounds__(256) k_sp_group_elect(SelfPlayDev d, uint32_t ply_epoch, int share)
+{
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= d.slots) return;
+    d.leader[s] = (int32_t)s;
+    d.search_active[s] = d.active[s];
+    if (!d.active[s]) return;
+    if (!share) { atomicAdd(&d.counters[6], 1ULL); return; }      // every live slot runs its own search
+    const uint32_t h = (uint32_t)(mix64(d.self_b[s] ^ mix64(d.opp_b[s] + 0x51ED270B27B4F3CFULL)) & d.r_mask);
+    d.root_h[s] = h;
+    atomicMin(&d.r_owner[h], ((unsigned long long)(~ply_epoch) << 32) | (unsigned long long)(uint32_t)s);
+}
+
+__global__ void __launch_bounds__(256) k_sp_group_follow(SelfPlayDev d)
+{
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= d.slots || !d.active[s]) return;
+    const uint32_t o = (uint32_t)(d.r_owner[d.root_h[s]] & 0xFFFFFFFFULL);
+    if (o != (uint32_t)s && d.self_b[o] == d.self_b[s] && d.opp_b[o] == d.opp_b[s]) {
+        d.leader[s] = (int32_t)o;           // same position: the leader's search is this slot's search
+        d.search_active[s] = 0;
+    } else {
+        atomicAdd(&d.counters[6], 1ULL);     // elected, or a different position on the same table entry
+    }
 }
 
 // One warp per slot: record the sample, choose and play the move, finish / refill the slot.
@@ -53,24 +87,25 @@ k_sp_move(SelfPlayDev d, TreeDev t, int64_t num_episodes, int threshold, uint64_
     uint64_t me = d.self_b[s], you = d.opp_b[s];
     const int ply = d.move_count[s];
     const int game = d.game_id[s];
-    const int first = t.node_first[s * t.node_cap], cnt = t.node_count[s * t.node_cap];
-    const int64_t ebase = s * (int64_t)t.edge_cap + first;
+    const int64_t ld = d.leader[s];                      // whose tree holds this slot's search (itself unless shared)
+    const int cnt = t.root_count[ld];
+    const Edge* E = t.edges + ld * (int64_t)t.edge_cap;
     oth_sample* smp = d.staging + s * kMaxPlies + (ply < kMaxPlies ? ply : kMaxPlies - 1);
     // ---- record (state, visit distribution, player) : parallel_self_play.py:364,385-388
     for (int j = lane; j < OTH_ACTIONS; j += 32) smp->visits[j] = 0;
     __syncwarp();
     int total = 0, best_k = 0, best_n = -1;
     for (int k = 0; k < cnt; ++k) {                      // <= 33 children: uniform loop, every lane keeps the stats
-        const int nv = t.edge_n[ebase + k];
+        const int nv = E[k].n;
         total += nv;
         if (nv > best_n) { best_n = nv; best_k = k; }    // np.argmax: first maximum (:380)
     }
-    for (int k = lane; k < cnt; k += 32) smp->visits[t.edge_action[ebase + k]] = (uint16_t)t.edge_n[ebase + k];
+    for (int k = lane; k < cnt; k += 32) smp->visits[E[k].action] = (uint16_t)E[k].n;
     if (lane == 0) {
         smp->self_b = me; smp->opp_b = you; smp->legal = legal_moves(me, you);
         smp->game = game; smp->ply = (int16_t)ply; smp->value = 0; smp->n_children = (uint8_t)cnt;
         smp->pad[0] = smp->pad[1] = smp->pad[2] = 0;
-        atomicAdd(&d.counters[4], (unsigned long long)t.n_evals[s]);
+        atomicAdd(&d.counters[4], (unsigned long long)t.n_evals[ld]);   // what the reference would have evaluated for this game
         if (ply >= kMaxPlies) atomicExch(&d.counters[5], 1ULL);
     }
     // ---- choose the move (:379-382)
@@ -80,12 +115,12 @@ k_sp_move(SelfPlayDev d, TreeDev t, int64_t num_episodes, int threshold, uint64_
         int target = (int)(((r >> 32) * (uint64_t)total) >> 32);   // uniform in [0,total)
         pick = cnt - 1;
         for (int k = 0; k < cnt; ++k) {
-            const int nv = t.edge_n[ebase + k];
+            const int nv = E[k].n;
             if (target < nv) { pick = k; break; }
             target -= nv;
         }
     }
-    const int action = t.edge_action[ebase + pick];
+    const int action = E[pick].action;
     apply_known_legal(me, you, action);                   // game.board.make_move(action) (:391)
     const int plies = ply + 1;
     const uint64_t lg = legal_moves(me, you);
@@ -139,6 +174,8 @@ struct SelfPlayHost {
     unsigned long long* h_counters = nullptr;   // pinned
     int64_t last_samples = 0;
     uint64_t moves_played = 0;
+    uint32_t ply_epoch = 0;
+    uint64_t last_searches = 0;
     unsigned long long last_stats[4] = {0, 0, 0, 0};
 
     int create(oth_ctx* c, const oth_selfplay_config* cf);
@@ -174,6 +211,14 @@ int SelfPlayHost::create(oth_ctx* c, const oth_selfplay_config* cf)
     if ((rc = grab((void**)&d.active, S))) return rc;
     if ((rc = grab((void**)&d.staging, S * kMaxPlies * sizeof(oth_sample)))) return rc;
     if ((rc = grab((void**)&d.counters, 8 * sizeof(unsigned long long)))) return rc;
+    if ((rc = grab((void**)&d.leader, S * 4))) return rc;
+    if ((rc = grab((void**)&d.search_active, S))) return rc;
+    if ((rc = grab((void**)&d.root_h, S * 4))) return rc;
+    uint64_t rcap = 1024;
+    while (rcap < 4 * (uint64_t)S) rcap <<= 1;
+    d.r_mask = rcap - 1;
+    if ((rc = grab((void**)&d.r_owner, rcap * sizeof(unsigned long long)))) return rc;
+    OTH_CHECK_CUDA(cudaMemsetAsync(d.r_owner, 0xFF, rcap * sizeof(unsigned long long), c->stream));
     OTH_CHECK_CUDA(cudaMallocHost((void**)&h_counters, 8 * sizeof(unsigned long long)));
     d.out = nullptr; d.out_cap = 0;
     return OTH_OK;
@@ -219,7 +264,18 @@ int SelfPlayHost::run(NetHost* net, int64_t num_episodes, int64_t* n_samples, in
     const int64_t max_moves = (num_episodes + d.slots - 1) / d.slots * kMaxPlies + kMaxPlies;
     for (int64_t mv = 0;; ++mv) {
         OTH_REQUIRE(mv <= max_moves, OTH_ERR_STATE, "oth_selfplay_run: games did not terminate");
-        int rc = search.begin(d.self_b, d.opp_b, d.active, d.slots);
+        // identical root positions share one search -- unless per-game Dirichlet noise really enters the search
+        const bool noisy = cfg.add_dirichlet_noise && (cfg.flags & OTH_FLAG_ROOT_N_SUM);
+        const int share = (!noisy && !(cfg.flags & OTH_FLAG_NO_SEARCH_SHARING)) ? 1 : 0;
+        ++ply_epoch;
+        k_sp_group_elect<<<grid_t, 256, 0, ctx->stream>>>(d, ply_epoch, share);
+        ctx->launches++;
+        if (share) {
+            k_sp_group_follow<<<grid_t, 256, 0, ctx->stream>>>(d);
+            ctx->launches++;
+        }
+        OTH_CHECK_CUDA(cudaGetLastError());
+        int rc = search.begin(d.self_b, d.opp_b, d.search_active, d.slots);
         if (rc) return rc;
         const uint64_t step_seed = mix64(cfg.seed + (uint64_t)mv * 0x9E3779B97F4A7C15ULL);
         if ((rc = search.run(net, cfg.num_simulations, cfg.add_dirichlet_noise != 0, step_seed))) return rc;
@@ -238,6 +294,7 @@ int SelfPlayHost::run(NetHost* net, int64_t num_episodes, int64_t* n_samples, in
     int rc = search.check_overflow();
     if (rc) return rc;
     if ((rc = search.read_stats(last_stats, false))) return rc;
+    last_searches = (uint64_t)h_counters[6];
     last_samples = (int64_t)h_counters[2];
     if (n_samples) *n_samples = last_samples;
     if (n_evals) *n_evals = (int64_t)h_counters[4];
@@ -284,6 +341,7 @@ int oth_selfplay_stats(oth_selfplay* sp, uint64_t* out4)
 {
     OTH_REQUIRE(sp && out4, OTH_ERR_ARG, "oth_selfplay_stats: NULL argument");
     for (int i = 0; i < 4; ++i) out4[i] = sp->last_stats[i];
+    out4[4] = sp->last_searches;
     return OTH_OK;
 }
 

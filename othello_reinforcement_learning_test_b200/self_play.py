@@ -68,10 +68,10 @@ class SelfPlayEngine:
         ns, ne = C.c_int64(0), C.c_int64(0)
         check(self.ctx.lib.oth_selfplay_run(self.handle, net_handle, int(num_episodes), C.byref(ns), C.byref(ne)))
         self.last_n_evals = int(ne.value)
-        st = (C.c_uint64 * 4)()
+        st = (C.c_uint64 * 5)()
         check(self.ctx.lib.oth_selfplay_stats(self.handle, st))
         self.last_stats = {"nn_positions": int(st[0]), "cache_hits": int(st[1]), "same_step_duplicates": int(st[2]),
-                           "hash_collisions": int(st[3])}
+                           "hash_collisions": int(st[3]), "searches_run": int(st[4])}
         out = np.empty(int(ns.value), _lib.SAMPLE_DTYPE)
         check(self.ctx.lib.oth_selfplay_fetch(self.handle, ptr(out), out.size, MEM_HOST))
         return out
@@ -103,7 +103,7 @@ class ParallelSelfPlayWorker:
                  dirichlet_epsilon: float = 0.25, *, concurrent_games: int | None = None, evaluator: str = "auto",
                  winner_black: bool = False, root_n_sum: bool = False, q_canonical: bool = False,
                  engine: str | None = None, seed: int | None = None, verbose: bool = True, eval_cache: bool = True,
-                 ctx: Context | None = None):
+                 share_searches: bool = True, ctx: Context | None = None):
         self.board_class = board_class
         self.num_simulations = num_simulations
         self.temperature_threshold = temperature_threshold
@@ -115,6 +115,7 @@ class ParallelSelfPlayWorker:
                                     dirichlet_epsilon=dirichlet_epsilon, evaluator=evaluator, root_n_sum=root_n_sum,
                                     q_canonical=q_canonical, engine=engine, eval_cache=eval_cache, ctx=ctx)
         self.winner_black = winner_black
+        self.share_searches = share_searches      # identical root positions run one search (same results)
         self.seed = seed
         self.verbose = verbose
         self._engine: SelfPlayEngine | None = None
@@ -127,7 +128,8 @@ class ParallelSelfPlayWorker:
 
     def _get_engine(self, num_episodes: int, add_noise: bool) -> SelfPlayEngine:
         m = self.batch_mcts
-        flags = m._flags() | (_lib.FLAG_WINNER_BLACK if self.winner_black else 0)
+        flags = m._flags() | (_lib.FLAG_WINNER_BLACK if self.winner_black else 0) | (
+            0 if self.share_searches else _lib.FLAG_NO_SEARCH_SHARING)
         seed = self.seed if self.seed is not None else int(np.random.randint(0, 2**31 - 1))
         key = (self._slots_for(num_episodes), self.num_simulations, self.temperature_threshold, m.c_puct,
                m.dirichlet_alpha, m.dirichlet_epsilon, bool(add_noise), flags, seed)

@@ -80,9 +80,17 @@ def test_eval_cache_and_dedup_are_result_transparent(ctx, golden_games):
     assert sa.size == sb.size and sa.tobytes() == sb.tobytes()
     st_a, st_b = a.last_stats, b.last_stats
     assert st_a["nn_evals"] == st_b["nn_evals"]                                       # expansions: same searches
-    assert st_a["nn_positions"] == st_a["nn_evals"] and st_a["cache_hits"] == 0
-    assert st_b["nn_positions"] + st_b["cache_hits"] + st_b["same_step_duplicates"] == st_b["nn_evals"]
-    assert st_b["cache_hits"] > 0.1 * st_b["nn_evals"] and st_b["same_step_duplicates"] > 0
+    # a = no cache but searches of identical roots are shared; c = nothing shared at all: one evaluation per expansion
+    c = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, "cuda", eval_cache=False, share_searches=False, **kw)
+    sc = c.execute_episodes_packed(160)
+    sc = sc[np.lexsort((sc["ply"], sc["game"]))]
+    assert sc.tobytes() == sa.tobytes()
+    st_c = c.last_stats
+    assert st_c["nn_positions"] == st_c["nn_evals"] == st_a["nn_evals"] and st_c["cache_hits"] == 0
+    assert st_c["searches_run"] == sc.size and st_a["searches_run"] < sc.size          # one search per recorded ply vs shared
+    assert st_a["nn_positions"] < st_a["nn_evals"] and st_a["cache_hits"] == 0
+    assert st_b["nn_positions"] < st_a["nn_positions"]
+    assert st_b["cache_hits"] > 0
     # second campaign on the same worker starts from an emptied cache and still agrees with the uncached engine
     sa2 = a.execute_episodes_packed(40); sb2 = b.execute_episodes_packed(40)
     sa2 = sa2[np.lexsort((sa2["ply"], sa2["game"]))]; sb2 = sb2[np.lexsort((sb2["ply"], sb2["game"]))]
@@ -94,3 +102,4 @@ def test_eval_cache_and_dedup_are_result_transparent(ctx, golden_games):
     assert np.array_equal(v0, v1) and np.array_equal(q0, q1) and np.array_equal(e0, e1)
     st = m1._tree.stats()
     assert st["nn_positions"] + st["cache_hits"] + st["same_step_duplicates"] == int(e1.sum())
+    assert st["cache_hits"] + st["same_step_duplicates"] > 0
