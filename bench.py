@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one self-play campaign: G concurrent games per GPU (default 75776 = 512 x 148 SMs) started
+A "step" is one self-play campaign: G concurrent games per GPU (default 151552 = 1024 x 148 SMs) started
 from the initial position and played to completion with the device-resident engine
 (ParallelSelfPlayWorker / oth_selfplay_run): per ply one search of 1 + 50 leaf evaluations per game
 (select -> tcgen05 ResNet -> expand/backup), move choice, trajectory recording, labelling.
@@ -237,6 +237,7 @@ def run_b200(args):
     # ---------------- timed: end to end through the public API (host buffers) ----------------
     h2d = d2h = 0
     e2e_ms = 0.0
+    replay = pkg.ReplayBuffer(max_size=int(G * 64 * world), ctx=ctx) if world > 1 else None
     barrier()
     for _ in range(args.steps):
         flush_l2()
@@ -244,9 +245,13 @@ def run_b200(args):
         if world > 1:
             h2d += 0 * odist.broadcast_weights(model, src=0)              # NCCL broadcast of the new weights
         net.sync_from(model, force=True)                                 # fold BN + bf16 pack + H2D
-        smp = worker.execute_episodes_packed(G, add_dirichlet_noise=True)   # campaign + D2H of the packed samples
-        if world > 1:
-            smp = odist.all_gather_samples(smp)                          # trajectories to every rank (replay buffer)
+        smp = worker.execute_episodes_packed(G, add_dirichlet_noise=True)   # campaign + D2H of this rank's packed samples
+        if world > 1:                                                    # trajectories of every rank into the replay buffer,
+            dptr, cnt = engine.samples_device()                          # NCCL all-gather device to device
+            gathered, total_cnt = odist.all_gather_samples_device(dptr, cnt, torch.device("cuda", local))
+            replay.clear()
+            pkg._lib.check(ctx.lib.oth_replay_add(replay.handle, gathered.data_ptr(), total_cnt, pkg._lib.MEM_DEVICE))
+            torch.cuda.synchronize()
         ev1.record(stream)
         ev1.synchronize()
         e2e_ms += ev0.elapsed_time(ev1)
@@ -327,7 +332,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--games", type=int, default=75776, help="concurrent games per GPU = games per step per GPU (512 x 148 SMs)")
+    ap.add_argument("--games", type=int, default=151552, help="concurrent games per GPU = games per step per GPU (1024 x 148 SMs)")
     ap.add_argument("--sims", type=int, default=50)
     ap.add_argument("--blocks", type=int, default=10)
     ap.add_argument("--filters", type=int, default=128)

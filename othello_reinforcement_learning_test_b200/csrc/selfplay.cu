@@ -193,7 +193,7 @@ int SelfPlayHost::create(oth_ctx* c, const oth_selfplay_config* cf)
     search.flags = cfg.flags;
     if (cfg.flags & OTH_FLAG_EVAL_CACHE) {
         uint64_t want = (uint64_t)cfg.concurrent_games * 2048ULL, cap = 1 << 16;
-        while (cap < want && cap < (1ULL << 26)) cap <<= 1;
+        while (cap < want && cap < (1ULL << 27)) cap <<= 1;
         if ((rc = search.enable_cache(cap))) return rc;
     }
     d.slots = cfg.concurrent_games;

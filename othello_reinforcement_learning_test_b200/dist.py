@@ -69,6 +69,35 @@ def all_gather_samples(samples: np.ndarray) -> np.ndarray:
     return out
 
 
+class _DevView:
+    """Zero-copy view of library-owned device memory for torch (CUDA array interface)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def all_gather_samples_device(dev_ptr: int, count: int, device: torch.device):
+    """All-gather packed samples that already live in device memory (oth_selfplay_samples_device) without a host
+    hop: returns (uint8 CUDA tensor holding every rank's records back to back in rank order, total count).
+    Feed it to a device ReplayBuffer with `oth_replay_add(..., OTH_MEM_DEVICE)`."""
+    world = dist.get_world_size()
+    rec = SAMPLE_DTYPE.itemsize
+    cnt = torch.tensor([count], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt)
+    counts = [int(c.item()) for c in counts]
+    biggest = max(max(counts), 1)
+    mine = torch.zeros(biggest * rec, dtype=torch.uint8, device=device)
+    if count:
+        mine[: count * rec] = torch.as_tensor(_DevView(dev_ptr, count * rec), device=device)
+    gathered = torch.empty(world * biggest * rec, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(gathered, mine)
+    if all(c == biggest for c in counts):
+        return gathered, sum(counts)
+    packed = torch.cat([gathered[r * biggest * rec: r * biggest * rec + c * rec] for r, c in enumerate(counts)])
+    return packed, sum(counts)
+
+
 def renumber_games(samples_per_rank: list[np.ndarray]) -> np.ndarray:
     """Concatenate per-rank sample arrays giving every episode a globally unique id."""
     out, base = [], 0
