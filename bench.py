@@ -106,6 +106,37 @@ def cpu_arm(args, model_sd, budget_s: float, threads=None):
                                                   mean_plies_per_game=MEAN_PLIES, seed=1)
 
 
+def cpu_playout_baseline():
+    """BASELINE config 1 on the host: the reference's own Cython bitboard in benchmark.py's loop (1 thread, from
+    oracle/_ref when it travelled) and the C restatement on 1 and on all threads."""
+    import random as _r
+    from oracle import cref, refload
+    out = {}
+    t0 = time.perf_counter(); r1 = cref.random_playouts(20000, 1, threads=1); dt = time.perf_counter() - t0
+    out["c_restatement_1_thread_games_per_s"] = 20000 / dt
+    n = 200000
+    t0 = time.perf_counter(); cref.random_playouts(n, 2, threads=0); dt = time.perf_counter() - t0
+    out["c_restatement_all_threads_games_per_s"] = n / dt
+    out["threads"] = os.cpu_count()
+    try:
+        Board = refload.ref_bitboard_class()
+        if Board is not None:
+            def play():                                   # benchmark.py:18-40
+                b = Board()
+                while not b.is_terminal():
+                    lm = b.get_legal_moves()
+                    b.make_move(64 if lm == [64] else _r.choice(lm))
+            for _ in range(50):
+                play()
+            t0 = time.perf_counter()
+            for _ in range(1000):
+                play()
+            out["reference_cython_1_thread_games_per_s"] = 1000 / (time.perf_counter() - t0)
+    except Exception as e:      # the compiled reference is a convenience, never a requirement
+        out["reference_cython_error"] = str(e)[:120]
+    return out
+
+
 def build_model(args):
     import torch
     from othello_reinforcement_learning_test_b200.net import OthelloResNet
@@ -301,11 +332,27 @@ def run_b200(args):
             "kernel_share_of_step": net_ms / total_ms if total_ms else None,
             "tree_kernels_ms_total": timing["tree"][0], "move_kernels_ms_total": timing["move"][0]}
 
+    # ---- secondary rooflines: tree kernels and random playouts against the HBM roofline ----
+    tree_ms = timing["tree"][0]
+    tree_bytes = float(evals) * 750.0                      # ~0.75 KB of tree traffic per simulation (select + expand + backup)
+    playout_bytes = n_po * 20.0                            # 16 B final board + 4 B ply count per game; state lives in registers
+    secondary = {
+        "tree_kernels": {"bound": "hbm", "algorithmic_bytes": tree_bytes, "ms": tree_ms,
+                         "achieved": tree_bytes / (tree_ms / 1e3) / 1e9 if tree_ms else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": (tree_bytes / (tree_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if tree_ms else None,
+                         "note": "pointer-chasing, latency-bound: one dependent 24-byte-record load per tree level; "
+                                 "searches of identical roots are shared, so fewer simulations run than are accounted"},
+        "random_playout": {"bound": "int-pipe (nominally hbm)", "algorithmic_bytes": playout_bytes, "ms": po_ms,
+                           "achieved": playout_bytes / (po_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "frac": playout_bytes / (po_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+                           "plies_per_s": po["total_plies"] / (po_ms / 1e3),
+                           "note": "whole game in registers: ~36k integer ops per game, 20 B of HBM traffic; the bound is the INT pipe"}}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config_dict(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
-            "gpu_launches": int(tot[2].item()), "clocks": clocks, "roofline": roof,
+            "gpu_launches": int(tot[2].item()), "clocks": clocks, "roofline": roof, "secondary_rooflines": secondary,
             "expansions_per_game": float(tot[1].item()) / games_total, "samples_per_game": float(tot[0].item()) / games_total,
             "eval_cache": {"enabled": not args.no_eval_cache, "rank0_expansions": int(evals), "rank0_network_positions": int(cache_stats[0]),
                            "rank0_cache_hits": int(cache_stats[1]), "rank0_same_step_duplicates": int(cache_stats[2]),
@@ -318,6 +365,7 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_arm(args, model.state_dict(), budget_s=args.cpu_seconds)
         line["cpu_baseline"] = {"value": r["games_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": r["sample"]}
+        line["random_playout"]["cpu"] = cpu_playout_baseline()
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)

@@ -17,6 +17,9 @@ if [ "${NCU:-1}" = "1" ]; then
   timeout 300 python tools/net_bench.py --n 18944 --reps 20 > "$OUT/net_bench.json" 2>&1 && \
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_net_tc -s 3 -c 1 -o "$OUT/prof_net_tc_fullbatch" -f python tools/net_bench.py --n 18944 --reps 2 > "$OUT/ncu_net_bench.log" 2>&1
   echo "ncu net_bench rc=$?" | tee -a "$OUT/summary.txt"
+  timeout 120 python tools/playout_bench.py 4194304 > "$OUT/playout_bench.json" 2>&1 && \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_playouts -s 1 -c 1 -o "$OUT/prof_playouts" -f python tools/playout_bench.py 4194304 > "$OUT/ncu_playouts.log" 2>&1
+  echo "ncu playouts rc=$?" | tee -a "$OUT/summary.txt"
   timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_tree_select|k_tree_expand|k_tree_assign|k_playouts" -s 300 -c 8 -o "$OUT/prof_tree" -f $NCU_CMD > "$OUT/ncu_tree.log" 2>&1
   echo "ncu tree rc=$?" | tee -a "$OUT/summary.txt"
 fi
