@@ -43,11 +43,32 @@ def _ensure_package(name: str) -> types.ModuleType:
     return mod
 
 
-def install(force: bool = True) -> None:
-    """Route the hot-path module names of the reference to this package."""
+_OPTIONAL = {
+    # the rows SURVEY.md 8(f) marks "next": opt in with install(replay_buffer=True, arena=True)
+    "replay_buffer": {"src.train.buffer": ("othello_reinforcement_learning_test_b200.buffer", ["ReplayBuffer", "PrioritizedReplayBuffer"])},
+    "arena": {"src.eval.arena": ("othello_reinforcement_learning_test_b200.arena", ["MatchResult", "BatchArena", "evaluate_player"]),
+              "src.eval.players": ("othello_reinforcement_learning_test_b200.arena", ["RandomPlayer", "GreedyPlayer", "MCTSPlayer"])},
+}
+
+
+def install(force: bool = True, replay_buffer: bool = False, arena: bool = False) -> None:
+    """Route the hot-path module names of the reference to this package.
+
+    replay_buffer=True also routes `src.train.buffer` (trainer.py imports ReplayBuffer from there) to the
+    device-resident buffer; arena=True routes `src.eval.arena` / `src.eval.players` to the batched arena
+    (its `Arena` name is `BatchArena`; players take and return whole batches as well as single boards)."""
+    extra = {}
+    if replay_buffer:
+        extra.update(_OPTIONAL["replay_buffer"])
+    if arena:
+        extra.update(_OPTIONAL["arena"])
+    _install_table({**_REPLACED, **extra}, force)
+
+
+def _install_table(table, force):
     from . import mcts as _mcts, self_play as _sp   # noqa: F401
     _sp.BatchMCTS = _mcts.BatchMCTS                  # the reference keeps BatchMCTS in parallel_self_play.py
-    for name, (target, names) in _REPLACED.items():
+    for name, (target, names) in table.items():
         if not force and name in sys.modules:
             continue
         parts = name.split(".")
@@ -64,7 +85,7 @@ def install(force: bool = True) -> None:
 
 
 def uninstall() -> None:
-    for name in _REPLACED:
+    for name in list(_REPLACED) + [k for t in _OPTIONAL.values() for k in t]:
         mod = sys.modules.get(name)
         if mod is not None and getattr(mod, "__b200_dropin__", False):
             del sys.modules[name]
