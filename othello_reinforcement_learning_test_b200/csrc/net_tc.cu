@@ -5,10 +5,13 @@
 // live in TMEM, and only the BN-folded bf16 weights stream in (L2-resident, 1-D bulk-TMA
 // copies into a 3-slot ring, each slot consumed by both tiles).
 //
-//   warps 0-3 : tile 0 epilogue (TMEM -> +bias/+skip/ReLU -> bf16 -> shared), input planes, heads
-//   warps 4-7 : tile 1 epilogue, same
-//   warp  8   : weight producer (one lane issues cp.async.bulk + mbarrier expect_tx)
-//   warp  9   : MMA issuer (one lane issues tcgen05.mma / tcgen05.commit), owns the TMEM allocation
+//   warps 0-3  : tile 0 epilogue (TMEM -> +bias/+skip/ReLU -> bf16 -> shared), input planes; the last layer's
+//                epilogue also applies the three 1x1 head convolutions to the row it holds in registers
+//   warps 4-7  : tile 1 epilogue, same
+//   warp  8    : weight producer (one lane issues cp.async.bulk + mbarrier expect_tx)
+//   warp  9    : MMA issuer (one lane issues tcgen05.mma / tcgen05.commit), owns the TMEM allocation
+//   warps 10,11: head warps (one per tile): policy fc + log-softmax + mask, value fc1/fc2 + tanh, output stores --
+//                they run while the tensor core is already busy with the NEXT item's trunk
 //
 // A 3x3 tap is not materialised (no im2col): the activation tile is stored K-major without
 // swizzle (net_common.cuh) so that tap (dy,dx) is the SAME UMMA shared-memory descriptor with
@@ -26,8 +29,14 @@ namespace oth {
 namespace tc {
 
 constexpr int kComputeWarps = 8;
-constexpr int kThreads = (kComputeWarps + 2) * 32;   // 320
+constexpr int kHeadWarp0 = kComputeWarps + 2;        // first head warp
+constexpr int kThreads = (kComputeWarps + 4) * 32;   // 384
 constexpr int kStages = 3;
+// named (hardware) barriers: 0 is __syncthreads
+constexpr int kBarAll = 1;        // the 8 epilogue warps
+constexpr int kBarTile = 2;       // +tile: the 4 epilogue warps of a tile
+constexpr int kBarHeadFull = 4;   // +tile: epilogue warps arrive, head warp syncs -- 1x1-conv outputs are in HeadScratch
+constexpr int kBarHeadFree = 6;   // +tile: head warp arrives, epilogue warps sync -- HeadScratch may be overwritten
 constexpr int kStagesPerConv = 18;                   // 2 channel halves x 9 taps
 
 template <int F>
@@ -48,9 +57,10 @@ struct Cfg {
     static constexpr int offBars = offHeads + 2 * (int)sizeof(HeadScratch);
     static constexpr int kNumBars = 2 * kStages + 2 + 4;
     static constexpr int offMisc = offBars + kNumBars * 8;
-    static constexpr int offBias = offMisc + 128;           // [tile][layer parity][F] fp32 bias of the layer in flight
-    static constexpr int kSmemBytes = offBias + 4 * F * 4;
-    static_assert(offBias % 16 == 0, "bias staging must be 16-byte aligned");
+    static constexpr int offBias = offMisc + 144;           // [tile][layer parity][F] fp32 bias of the layer in flight
+    static constexpr int offHeadW = offBias + 4 * F * 4;    // [3][F] fp32: policy 1x1 (2 channels) and value 1x1 weights
+    static constexpr int kSmemBytes = offHeadW + 3 * F * 4;
+    static_assert(offBias % 16 == 0 && offHeadW % 16 == 0, "bias / head-weight staging must be 16-byte aligned");
     static_assert(sizeof(HeadScratch) % 16 == 0, "HeadScratch must keep 16-byte alignment");
     static_assert(kRingSlotBytes % 128 == 0, "ring slots must stay 128-byte aligned");
     static_assert(kSmemBytes <= 232448, "shared-memory budget (227 KB) exceeded");
@@ -60,77 +70,93 @@ struct Cfg {
 struct Misc {
     uint32_t tmem_base;
     uint32_t pad;
-    uint64_t s_self[4], s_opp[4], s_legal[4];
+    uint64_t s_self[4], s_opp[4];
+    uint64_t s_legal[2][4];      // by item parity: the head warps still need the previous item's masks
 };
+static_assert(sizeof(Misc) <= 144, "Misc slot");
 
-// Issue every MMA of one convolution for both tiles.  Fully unrolled: each operand descriptor is
-// "base + immediate" in 16-byte units (lo word = start>>4 | LBO>>4 << 16, hi word constant).
-// Called by all 32 lanes of the MMA warp (warp-uniform operands live in uniform registers); only the
-// elected lane issues.  K order of a trunk conv: channel half 0 for all nine taps, then half 1, so the
-// MMAs of half 0 can start as soon as the previous layer's epilogue has written channels [0, F/2).
+// Issue every MMA of one convolution for both tiles.  Called by all 32 lanes of the MMA warp: control flow and
+// operands are warp-uniform (they live in uniform registers), only the elected lane issues.  Each operand
+// descriptor is "base + immediate" in 16-byte units (lo word = start>>4 | LBO>>4 << 16, hi word constant; every
+// shared-memory address is below 2^18, so the 14-bit start field needs no masking).
+// K order of a trunk conv: channel half 0 for all nine taps, then half 1, so the MMAs of half 0 can start as
+// soon as the previous layer's epilogue has written channels [0, F/2).
+// Loop shape: one trip = one ring round = one tap row (3 taps = 3 ring slots, slot index == dx + 1), unrolled
+// inside, rolled outside.  Fully unrolled (144 MMAs) the issue code alone is 24 KB and fights the epilogue for
+// the instruction cache; fully rolled, the per-stage descriptor arithmetic lands on the issue critical path.
 template <int F, bool STEM>
 __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off, uint32_t d_col, uint64_t* bar_full,
                                             uint64_t* bar_empty, uint64_t* bar_acc, uint64_t* bar_act, uint32_t act_phase,
                                             uint32_t& round)
 {
     using C = Cfg<F>;
+    static_assert(kStages == 3 && kStagesPerConv == 18, "one ring round = one tap row");
     constexpr uint32_t idesc = umma_idesc(F);
-    constexpr int kStagesHere = STEM ? 3 : kStagesPerConv;
-    static_assert(kStagesHere % kStages == 0, "a layer must use whole ring rounds");
     constexpr uint32_t kAHi = (uint32_t)(kGroupUnits) | (1u << 14);                 // SBO = 144 B, version 1
     constexpr uint32_t kBHi = (uint32_t)(128 >> 4) | (1u << 14);                    // SBO = 128 B
     constexpr uint32_t kALboField = (uint32_t)kPlaneUnits << 16;                    // LBO = plane stride
     constexpr uint32_t kBLboField = (uint32_t)F << 16;                              // LBO = F rows x 16 B
-    const uint32_t a_row0 = ((smem_base + in_off) >> 4) + kGuardUnits + kHaloUnits; // unit index of row 0, plane 0, tile 0
-    const uint32_t ring0 = (smem_base + (uint32_t)C::offRing) >> 4;
+    constexpr uint32_t kSlotUnits = (uint32_t)(C::kRingSlotBytes >> 4);
+    constexpr uint32_t kTileUnits = (uint32_t)(C::kTileBytes >> 4);
+    // unit index of row 0, plane 0, tile 0, with the LBO field folded in
+    const uint32_t a_row0 = (((smem_base + in_off) >> 4) + kGuardUnits + kHaloUnits) | kALboField;
+    const uint32_t ring0 = ((smem_base + (uint32_t)C::offRing) >> 4) | kBLboField;
+    if (STEM) {
+        mbar_wait(&bar_act[0], act_phase); mbar_wait(&bar_act[1], act_phase);
+        mbar_wait(&bar_act[2], act_phase); mbar_wait(&bar_act[3], act_phase);
 #pragma unroll
-    for (int s = 0; s < kStagesHere; ++s) {
-        const int slot = s % kStages;
-        if (s > 0 && slot == 0) ++round;
-        if (STEM) {
-            if (s == 0) {
-                mbar_wait(&bar_act[0], act_phase); mbar_wait(&bar_act[1], act_phase);
-                mbar_wait(&bar_act[2], act_phase); mbar_wait(&bar_act[3], act_phase);
-            }
-        } else if (s % 9 == 0) {                                                    // first tap of a channel half
-            mbar_wait(&bar_act[0 + s / 9], act_phase);                              // tile 0, this half
-            mbar_wait(&bar_act[2 + s / 9], act_phase);                              // tile 1, this half
-        }
-        mbar_wait(&bar_full[slot], round & 1);
-        tc_fence_after();
-        if (elect_one()) {
-            const uint32_t wb = ring0 + (uint32_t)slot * (C::kRingSlotBytes >> 4);
+        for (int s = 0; s < 3; ++s) {                                               // stage s = tap row dy = s - 1, three taps
+            mbar_wait(&bar_full[s], round & 1);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-            for (int tile = 0; tile < 2; ++tile) {
-                const uint32_t d = d_col + (uint32_t)(tile * F);
-                const uint32_t a_tile = a_row0 + (uint32_t)tile * (C::kTileBytes >> 4);
-                if (STEM) {
+                for (int tile = 0; tile < 2; ++tile) {
 #pragma unroll
                     for (int t3 = 0; t3 < 3; ++t3) {
-                        const int tap = s * 3 + t3;
-                        const int shift = (tap / 3 - 1) * 2 * kGroupUnits + (tap % 3 - 1);
-                        const uint64_t ad = ((uint64_t)kAHi << 32) | (uint64_t)(((a_tile + shift) & 0x3FFFu) | kALboField);
-                        const uint64_t bd = ((uint64_t)kBHi << 32) | (uint64_t)(((wb + t3 * 2 * F) & 0x3FFFu) | kBLboField);
-                        umma_bf16(d, ad, bd, idesc, tap > 0 ? 1u : 0u);
+                        const uint32_t a_u = a_row0 + (uint32_t)(tile * kTileUnits + (s - 1) * 2 * kGroupUnits + (t3 - 1));
+                        const uint32_t b_u = ring0 + (uint32_t)(s * kSlotUnits + t3 * 2 * F);
+                        umma_bf16(d_col + (uint32_t)(tile * F), ((uint64_t)kAHi << 32) | a_u, ((uint64_t)kBHi << 32) | b_u, idesc,
+                                  (s > 0 || t3 > 0) ? 1u : 0u);
                     }
-                } else {
-                    const int half = s / 9, tap = s % 9;
-                    const int shift = (tap / 3 - 1) * 2 * kGroupUnits + (tap % 3 - 1);
-#pragma unroll
-                    for (int j = 0; j < C::kMmasPerStage; ++j) {
-                        const int kc = half * C::kPlanesPerHalf + 2 * j;
-                        const uint64_t ad = ((uint64_t)kAHi << 32) | (uint64_t)(((a_tile + kc * kPlaneUnits + shift) & 0x3FFFu) | kALboField);
-                        const uint64_t bd = ((uint64_t)kBHi << 32) | (uint64_t)(((wb + 2 * j * F) & 0x3FFFu) | kBLboField);
-                        umma_bf16(d, ad, bd, idesc, (s > 0 || j > 0) ? 1u : 0u);
-                    }
+                    if (s == 2) umma_commit(&bar_acc[tile]);
                 }
-                if (s == kStagesHere - 1) umma_commit(&bar_acc[tile]);   // this tile's accumulator is complete
+                umma_commit(&bar_empty[s]);
             }
-            umma_commit(&bar_empty[slot]);                                // slot free once both tiles have read it
+            __syncwarp();
         }
-        __syncwarp();
+        ++round;
+    } else {
+#pragma unroll 1
+        for (int r = 0; r < 6; ++r) {                                               // r = half * 3 + tap row
+            const int half = r >= 3 ? 1 : 0, ty = r - 3 * half;
+            if (ty == 0) {                                                          // first tap of a channel half
+                mbar_wait(&bar_act[0 + half], act_phase);                           // tile 0, this half
+                mbar_wait(&bar_act[2 + half], act_phase);                           // tile 1, this half
+            }
+            const uint32_t a_base = a_row0 + (uint32_t)(half * C::kPlanesPerHalf * kPlaneUnits + (ty - 1) * 2 * kGroupUnits - 1);
+#pragma unroll
+            for (int sl = 0; sl < 3; ++sl) {                                        // ring slot == tap column
+                mbar_wait(&bar_full[sl], round & 1);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int tile = 0; tile < 2; ++tile) {
+#pragma unroll
+                        for (int j = 0; j < C::kMmasPerStage; ++j) {
+                            const uint32_t a_u = a_base + (uint32_t)(tile * kTileUnits + 2 * j * kPlaneUnits + sl);
+                            const uint32_t b_u = ring0 + (uint32_t)(sl * kSlotUnits + 2 * j * F);
+                            umma_bf16(d_col + (uint32_t)(tile * F), ((uint64_t)kAHi << 32) | a_u, ((uint64_t)kBHi << 32) | b_u, idesc,
+                                      (sl > 0 || j > 0) ? 1u : (r > 0 ? 1u : 0u));
+                        }
+                        if (sl == 2 && r == 5) umma_commit(&bar_acc[tile]);       // this tile's accumulator is complete
+                    }
+                    umma_commit(&bar_empty[sl]);                                    // slot free once both tiles have read it
+                }
+                __syncwarp();
+            }
+            ++round;
+        }
     }
-    ++round;
 }
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32])
@@ -147,10 +173,13 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
         : "memory");
 }
 
-// 32 accumulator columns of one GEMM row -> +bias (+skip) -> ReLU -> bf16 -> four 16-byte stores
-template <bool SKIP>
+// 32 accumulator columns of one GEMM row -> +bias (+skip) -> ReLU -> bf16 -> four 16-byte stores.
+// LAST (final trunk layer): instead of storing, feed the bf16-rounded activations to the three 1x1 head
+// convolutions (net.py:85,121), channels in ascending order, accumulators carried in hp[3].
+template <bool SKIP, bool LAST>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int chunk, int m, const float* bias_s,
-                                               const uint4* __restrict__ resid, uint4* __restrict__ out)
+                                               const uint4* __restrict__ resid, uint4* __restrict__ out,
+                                               const float* __restrict__ head_w, int F, float (&hp)[3])
 {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -170,7 +199,133 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int chun
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-        out[u] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        const uint4 packed = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        if (LAST) {
+            const float x[8] = {bf16_lo(packed.x), bf16_hi(packed.x), bf16_lo(packed.y), bf16_hi(packed.y),
+                                bf16_lo(packed.z), bf16_hi(packed.z), bf16_lo(packed.w), bf16_hi(packed.w)};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = kc * 8 + j;
+                hp[0] = fmaf(x[j], head_w[c], hp[0]);
+                hp[1] = fmaf(x[j], head_w[F + c], hp[1]);
+                hp[2] = fmaf(x[j], head_w[2 * F + c], hp[2]);
+            }
+        } else {
+            out[u] = packed;
+        }
+    }
+}
+
+// The part of the heads after the 1x1 convolutions (net.py:86-94,122-134) for the two boards of one tile, run by
+// ONE warp: policy fc (128 -> 65), log-softmax (+exp, +action mask and renormalisation), value fc1 (64 -> 256, ReLU),
+// fc2 (256 -> 1), tanh.  Same operation order per output as heads_for_tile (net_common.cuh), so both engines
+// return identical bits.  Lane l owns policy outputs l, l+32 (and 64, computed by every lane) and hidden units l+32r.
+__device__ __forceinline__ void heads_tail_warp(const NetDev& net, HeadScratch* hs, const uint64_t* s_legal, int64_t board0,
+                                                int64_t n_boards, float* __restrict__ policy_out,
+                                                float* __restrict__ value_out, int out_kind, int lane)
+{
+    float pa[kBoardsPerTile][3];
+    {
+        const float b0 = __ldg(net.pfc_b + lane), b1 = __ldg(net.pfc_b + 32 + lane), b2 = __ldg(net.pfc_b + 64);
+#pragma unroll
+        for (int b = 0; b < kBoardsPerTile; ++b) { pa[b][0] = b0; pa[b][1] = b1; pa[b][2] = b2; }
+    }
+#pragma unroll 8
+    for (int i = 0; i < 128; ++i) {
+        const float w0 = __ldg(net.pfc_t + i * 65 + lane), w1 = __ldg(net.pfc_t + i * 65 + 32 + lane), w2 = __ldg(net.pfc_t + i * 65 + 64);
+#pragma unroll
+        for (int b = 0; b < kBoardsPerTile; ++b) {
+            const float x = hs->pol_in[b][i];
+            pa[b][0] = fmaf(x, w0, pa[b][0]); pa[b][1] = fmaf(x, w1, pa[b][1]); pa[b][2] = fmaf(x, w2, pa[b][2]);
+        }
+    }
+    float ha[kBoardsPerTile][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const float bb = __ldg(net.v1_b + 32 * r + lane);
+#pragma unroll
+        for (int b = 0; b < kBoardsPerTile; ++b) ha[b][r] = bb;
+    }
+#pragma unroll 4
+    for (int i = 0; i < 64; ++i) {
+        float w[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) w[r] = __ldg(net.v1_t + i * 256 + 32 * r + lane);
+#pragma unroll
+        for (int b = 0; b < kBoardsPerTile; ++b) {
+            const float x = hs->val_in[b][i];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) ha[b][r] = fmaf(x, w[r], ha[b][r]);
+        }
+    }
+    float v2w[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v2w[r] = __ldg(net.v2_w + 32 * r + lane);
+    const float v2b = __ldg(net.v2_b);
+#pragma unroll
+    for (int b = 0; b < kBoardsPerTile; ++b) {
+        const int64_t board = board0 + b;
+        // log_softmax over the 65 logits (net.py:94)
+        float mx = fmaxf(fmaxf(-INFINITY, pa[b][0]), pa[b][1]);
+        if (lane == 0) mx = fmaxf(mx, pa[b][2]);
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        float se = 0.f;
+        se += expf(pa[b][0] - mx);
+        se += expf(pa[b][1] - mx);
+        if (lane == 0) se += expf(pa[b][2] - mx);
+        for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xFFFFFFFFu, se, o);
+        const float lse = logf(se);
+        float out3[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const float logp = (pa[b][q] - mx) - lse;
+            out3[q] = (out_kind == kOutLogProbs) ? logp : expf(logp);
+        }
+        // value head: fc1 ReLU, fc2, tanh (net.py:128-134)
+        float part = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) part = fmaf(fmaxf(ha[b][r], 0.f), v2w[r], part);
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+        if (out_kind == kOutPriors) {
+            // MCTSNode.expand's masking (node.py:71-80) with numpy's float32 summation order, spread over the warp
+            const uint64_t legal = s_legal[b];
+            const bool pass_only = legal == 0;
+            if (pass_only) { out3[0] = 0.f; out3[1] = 0.f; }
+            else {
+                if (!((legal >> lane) & 1ULL)) out3[0] = 0.f;
+                if (!((legal >> (32 + lane)) & 1ULL)) out3[1] = 0.f;
+                out3[2] = 0.f;
+            }
+            // np_sum65: accumulator k (k = 0..7) adds p[k], p[8+k], ..., p[56+k]; p[j] lives in lane j&31, slot j>>5
+            float racc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; i += 8) {
+                const float v = __shfl_sync(0xFFFFFFFFu, (i & 32) ? out3[1] : out3[0], (i & 31) + (lane & 7));
+                racc = (i == 0) ? v : __fadd_rn(racc, v);
+            }
+            float rr[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rr[k] = __shfl_sync(0xFFFFFFFFu, racc, k);
+            float total = __fadd_rn(__fadd_rn(__fadd_rn(rr[0], rr[1]), __fadd_rn(rr[2], rr[3])),
+                                    __fadd_rn(__fadd_rn(rr[4], rr[5]), __fadd_rn(rr[6], rr[7])));
+            total = __fadd_rn(total, __shfl_sync(0xFFFFFFFFu, out3[2], 0));
+            if (total > 0.f) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) out3[q] = __fdiv_rn(out3[q], total);
+            } else {
+                const float u = (float)(1.0 / (double)(pass_only ? 1 : popc64(legal)));
+                if (pass_only) out3[2] = u;
+                else {
+                    if ((legal >> lane) & 1ULL) out3[0] = u;
+                    if ((legal >> (32 + lane)) & 1ULL) out3[1] = u;
+                }
+            }
+        }
+        if (board < n_boards) {
+            policy_out[board * 65 + lane] = out3[0];
+            policy_out[board * 65 + 32 + lane] = out3[1];
+            if (lane == 0) { policy_out[board * 65 + 64] = out3[2]; value_out[board] = tanhf(part + v2b); }
+        }
     }
 }
 
@@ -187,6 +342,7 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
     uint64_t* bar_empty = bars + kStages;            // [kStages] slot consumed by the tensor core
     uint64_t* bar_acc = bars + 2 * kStages;          // [2] accumulator tile complete
     uint64_t* bar_act = bars + 2 * kStages + 2;      // [tile*2 + half] activation half-tile written (128 arrivals)
+    float* head_w = reinterpret_cast<float*>(smem + C::offHeadW);
     Misc* misc = reinterpret_cast<Misc*>(smem + C::offMisc);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -199,6 +355,8 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
         for (int i = 0; i < 4; ++i) mbar_init(&bar_act[i], 128);
         fence_barrier_init();
     }
+    for (int i = threadIdx.x; i < 3 * F; i += kThreads)
+        head_w[i] = i < 2 * F ? __ldg(net.ph_w + i) : __ldg(net.vh_w + (i - 2 * F));
     if (warp == kComputeWarps + 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc->tmem_base)),
                      "r"((uint32_t)C::kTmemCols)
@@ -217,20 +375,21 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
         const int tt = threadIdx.x & 127;                 // thread index within the tile's 128 threads
         uint4* bufA = reinterpret_cast<uint4*>(smem + C::offA + tile * C::kTileBytes);
         uint4* bufB = reinterpret_cast<uint4*>(smem + C::offB + tile * C::kTileBytes);
-        HeadScratch* hs = reinterpret_cast<HeadScratch*>(smem + C::offHeads) + tile;
         zero_tile_buffer(bufA, C::KC, tt, 128);
         zero_tile_buffer(bufB, C::KC, tt, 128);
         uint32_t acc_phase = 0;
         uint32_t layer_count = 0;                         // accumulator buffer parity runs across items
-        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-            named_bar_sync(1, kComputeWarps * 32);        // previous item's heads are done with misc->s_*
+        uint32_t it = 0;                                  // items done by this CTA
+        const float ph_b0 = __ldg(net.ph_b), ph_b1 = __ldg(net.ph_b + 1), vh_b = __ldg(net.vh_b);
+        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            named_bar_sync(kBarAll, kComputeWarps * 32);        // everybody is done reading the previous item's misc->s_self/opp
             if (threadIdx.x < 4) {
                 const int64_t b = item * 4 + threadIdx.x;
                 const uint64_t a = b < n ? self_b[b] : 0ULL, o = b < n ? opp_b[b] : 0ULL;
-                misc->s_self[threadIdx.x] = a; misc->s_opp[threadIdx.x] = o; misc->s_legal[threadIdx.x] = legal_moves(a, o);
+                misc->s_self[threadIdx.x] = a; misc->s_opp[threadIdx.x] = o; misc->s_legal[it & 1][threadIdx.x] = legal_moves(a, o);
             }
-            named_bar_sync(1, kComputeWarps * 32);
-            build_input_row(bufA, m, misc->s_self + 2 * tile, misc->s_opp + 2 * tile, misc->s_legal + 2 * tile);
+            named_bar_sync(kBarAll, kComputeWarps * 32);
+            build_input_row(bufA, m, misc->s_self + 2 * tile, misc->s_opp + 2 * tile, misc->s_legal[it & 1] + 2 * tile);
             bufA[unit_of_row(1, m)] = make_uint4(0, 0, 0, 0);   // K padding plane of the stem
             fence_async_proxy();
             mbar_arrive(&bar_act[tile * 2 + 0]);
@@ -238,16 +397,21 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
             for (int layer = 0; layer < n_layers; ++layer, ++layer_count) {
                 const bool into_b = (layer == 0) || ((layer & 1) == 0);   // stem and conv2 write the residual stream
                 const bool skip = layer > 0 && (layer & 1) == 0;          // conv2: add the block input
+                const bool last = layer + 1 == n_layers;
                 uint4* out = into_b ? bufB : bufA;
                 // stage this layer's bias in shared memory while the tensor core is still busy
                 float* bias_s = reinterpret_cast<float*>(smem + C::offBias) + (tile * 2 + (layer & 1)) * F;
                 if (tt < F) bias_s[tt] = __ldg(net.bias + (size_t)layer * F + tt);
-                named_bar_sync(2 + tile, 128);
-                mbar_wait(&bar_acc[tile], acc_phase);
+                // One warp per tile watches the mbarrier and releases the other three through a named barrier: warps
+                // parked in mbarrier.try_wait are not free -- every additional long-term waiter measurably slows the
+                // MMA / weight pipeline of the whole SM, whereas bar.sync waiters cost nothing.
+                if ((warp & 3) == 0) mbar_wait(&bar_acc[tile], acc_phase);
+                named_bar_sync(kBarTile + tile, 128);
                 acc_phase ^= 1;
                 tc_fence_after();
                 if (net.trace && blockIdx.x == 0 && tt == 0) net.trace[layer * 8 + 2 + 2 * tile] = clock64();
                 const uint32_t tcol = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((layer_count & 1) * 2 * F + tile * F);
+                float hp[3] = {0.f, 0.f, 0.f};
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     // channels [half*F/2, (half+1)*F/2): load them all, then convert; the next layer's MMAs over this
@@ -259,20 +423,30 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int c = 0; c < kChunks; ++c) {
-                        if (skip) epilogue_chunk<true>(r[c], half * kChunks + c, m, bias_s, bufB, out);
-                        else epilogue_chunk<false>(r[c], half * kChunks + c, m, bias_s, bufB, out);
+                        if (last) {
+                            if (skip) epilogue_chunk<true, true>(r[c], half * kChunks + c, m, bias_s, bufB, out, head_w, F, hp);
+                            else epilogue_chunk<false, true>(r[c], half * kChunks + c, m, bias_s, bufB, out, head_w, F, hp);
+                        } else if (skip) epilogue_chunk<true, false>(r[c], half * kChunks + c, m, bias_s, bufB, out, head_w, F, hp);
+                        else epilogue_chunk<false, false>(r[c], half * kChunks + c, m, bias_s, bufB, out, head_w, F, hp);
                     }
                     tc_fence_before();
-                    if (layer + 1 < n_layers) {
+                    if (!last) {
                         fence_async_proxy();                  // generic-proxy stores -> visible to the tensor core
                         mbar_arrive(&bar_act[tile * 2 + half]);
                     }
                 }
+                if (last) {
+                    // hand the 1x1-conv outputs (ReLU'd, flattened channel-major, net.py:90) to this tile's head warp
+                    HeadScratch* hs = reinterpret_cast<HeadScratch*>(smem + C::offHeads) + tile;
+                    const int b = (m >> 3) & 1, sq = ((m >> 4) << 3) | (m & 7);
+                    named_bar_sync(kBarHeadFree + tile, 160);                // previous item's heads are done with the scratch
+                    hs->pol_in[b][sq] = fmaxf(hp[0] + ph_b0, 0.f);
+                    hs->pol_in[b][64 + sq] = fmaxf(hp[1] + ph_b1, 0.f);
+                    hs->val_in[b][sq] = fmaxf(hp[2] + vh_b, 0.f);
+                    named_bar_arrive(kBarHeadFull + tile, 160);
+                }
                 if (net.trace && blockIdx.x == 0 && tt == 0) net.trace[layer * 8 + 3 + 2 * tile] = clock64();
             }
-            named_bar_sync(2 + tile, 128);                // final activations of this tile are complete
-            heads_for_tile(net, bufB, hs, misc->s_legal + 2 * tile, item * 4 + 2 * tile, n, policy_out, value_out, out_kind, tt,
-                           128, [tile] { named_bar_sync(2 + tile, 128); });
         }
     } else if (warp == kComputeWarps) {
         // ===================== weight producer =====================
@@ -295,13 +469,26 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
             }
         }
         __syncwarp();
+    } else if (warp >= kHeadWarp0) {
+        // ===================== head warps =====================
+        const int tile = warp - kHeadWarp0;
+        HeadScratch* hs = reinterpret_cast<HeadScratch*>(smem + C::offHeads) + tile;
+        uint32_t it = 0;
+        // named barriers, not mbarriers (see the note at the accumulator wait): 128 epilogue threads + this warp
+        named_bar_arrive(kBarHeadFree + tile, 160);                           // the scratch starts out free
+        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            named_bar_sync(kBarHeadFull + tile, 160);
+            heads_tail_warp(net, hs, misc->s_legal[it & 1] + 2 * tile, item * 4 + 2 * tile, n, policy_out, value_out, out_kind, lane);
+            __syncwarp();
+            if (item + gridDim.x < n_items) named_bar_arrive(kBarHeadFree + tile, 160);
+        }
     } else {
         // ===================== MMA issuer =====================
         // The whole warp runs the loop (warp-uniform control flow and operands, so descriptors live in
         // uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit.
         const uint32_t smem_base = smem_u32(smem);
         const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
-        uint32_t round = 0, act_phase = 0, layer_count = 0;      // ring round: every layer uses a multiple of kStages stages
+        uint32_t round = 0, act_phase = 0, layer_count = 0;      // ring round: every layer uses whole ring rounds
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             for (int layer = 0; layer < n_layers; ++layer, ++layer_count) {
                 const bool from_a = (layer == 0) || ((layer & 1) == 0);   // stem reads the input, conv2 reads h: both in A
