@@ -86,13 +86,13 @@ int NetHost::load(const float* flat, int64_t count)
                     if (ci < cin) v = w[((int64_t)co * cin + ci) * 9 + tap] * scale[co];
                     const uint16_t h = f32_to_bf16_rne(v);
                     // UMMA B tiles, K-major, no swizzle.  Stem: [tap][kc][cout][8].  Trunk: the kernel walks K as
-                    // (channel half, tap, plane) so the first half can start early: [half][tap][plane in half][cout][8].
+                    // (32-channel split, tap, plane) so a split can start early: [split][tap][plane in split][cout][8].
                     size_t idx;
                     if (conv == 0) {
                         idx = (((size_t)tap * kcp + ci / 8) * F + co) * 8 + (ci % 8);
                     } else {
-                        const int pph = kcp / 2, plane = ci / 8, half = plane / pph, pl = plane % pph;
-                        idx = ((((size_t)half * 9 + tap) * pph + pl) * F + co) * 8 + (ci % 8);
+                        const int pps = 4, plane = ci / 8, split = plane / pps, pl = plane % pps;
+                        idx = ((((size_t)split * 9 + tap) * pps + pl) * F + co) * 8 + (ci % 8);
                     }
                     wtc[tc_off + idx] = h;
                     if (ci < cin_simt) wsimt[simt_off + ((size_t)tap * cin_simt + ci) * F + co] = bf16_to_f32(h);

@@ -3,7 +3,7 @@
 // One persistent CTA per SM walks over "items" of 4 boards (2 tiles x 128 GEMM rows).  The
 // whole network runs inside the kernel: activations never leave shared memory, accumulators
 // live in TMEM, and only the BN-folded bf16 weights stream in (L2-resident, 1-D bulk-TMA
-// copies into a 3-slot ring, each slot consumed by both tiles).
+// copies into a 6-slot ring, each slot consumed by both tiles).
 //
 //   warps 0-3  : tile 0 epilogue (TMEM -> +bias/+skip/ReLU -> bf16 -> shared), input planes; the last layer's
 //                epilogue also applies the three 1x1 head convolutions to the row it holds in registers
@@ -31,35 +31,40 @@ namespace tc {
 constexpr int kComputeWarps = 8;
 constexpr int kHeadWarp0 = kComputeWarps + 2;        // first head warp
 constexpr int kThreads = (kComputeWarps + 4) * 32;   // 384
-constexpr int kStages = 3;
+constexpr int kStages = 6;
 // named (hardware) barriers: 0 is __syncthreads
 constexpr int kBarAll = 1;        // the 8 epilogue warps
 constexpr int kBarTile = 2;       // +tile: the 4 epilogue warps of a tile
 constexpr int kBarHeadFull = 4;   // +tile: epilogue warps arrive, head warp syncs -- 1x1-conv outputs are in HeadScratch
 constexpr int kBarHeadFree = 6;   // +tile: head warp arrives, epilogue warps sync -- HeadScratch may be overwritten
-constexpr int kStagesPerConv = 18;                   // 2 channel halves x 9 taps
+constexpr int kSplitChannels = 32;                   // K walked as (32-channel split, tap): the next layer starts on a split
+                                                     // as soon as the epilogue has written those 32 channels
 
 template <int F>
 struct Cfg {
     static constexpr int KC = F / 8;                        // 8-channel planes
-    static constexpr int kPlanesPerHalf = KC / 2;
-    static constexpr int kMmasPerStage = F / 32;            // K = F/2 per (half, tap), 16 per MMA
+    static constexpr int kSplits = F / kSplitChannels;      // channel splits per conv (4 for F=128, 2 for F=64)
+    static constexpr int kPlanesPerSplit = kSplitChannels / 8;
+    static constexpr int kStagesPerConv = 9 * kSplits;      // one ring stage = one (split, tap)
+    static constexpr int kMmasPerStage = kSplitChannels / 16;
     static constexpr int kTileBytes = tile_buffer_bytes(KC);
-    static constexpr int kStageBytes = kPlanesPerHalf * F * 16;   // one tap, one channel half: [planes][F rows][8 ch]
-    static constexpr int kStemStageBytes = 3 * 2 * F * 16;  // 3 taps x 2 planes (K padded to 16)
+    static constexpr int kStageBytes = kPlanesPerSplit * F * 16;  // one tap, one split: [planes][F rows][8 ch]
+    static constexpr int kStemTapBytes = 2 * F * 16;        // one stem tap: 2 planes (K padded to 16)
     static constexpr int kTmemCols = 4 * F;                 // 2 tiles x 2 accumulator buffers (layer parity)
     // shared-memory map
     static constexpr int offA = 0;                          // A[2] : conv1 output h / network input
     static constexpr int offB = 2 * kTileBytes;             // B[2] : residual stream x
     static constexpr int offRing = 4 * kTileBytes;
-    static constexpr int kRingSlotBytes = kStageBytes > kStemStageBytes ? kStageBytes : kStemStageBytes;
+    static constexpr int kRingSlotBytes = kStageBytes;      // a stem stage is two taps or one: 2 * kStemTapBytes == kStageBytes
     static constexpr int offHeads = offRing + kStages * kRingSlotBytes;
     static constexpr int offBars = offHeads + 2 * (int)sizeof(HeadScratch);
-    static constexpr int kNumBars = 2 * kStages + 2 + 4;
+    static constexpr int kNumBars = 2 * kStages + 2 + 2 * kSplits;
     static constexpr int offMisc = offBars + kNumBars * 8;
     static constexpr int offBias = offMisc + 144;           // [tile][layer parity][F] fp32 bias of the layer in flight
     static constexpr int offHeadW = offBias + 4 * F * 4;    // [3][F] fp32: policy 1x1 (2 channels) and value 1x1 weights
     static constexpr int kSmemBytes = offHeadW + 3 * F * 4;
+    static_assert(2 * kStemTapBytes == kStageBytes, "stem stages reuse the trunk's ring slots");
+    static_assert(kStagesPerConv % (3 * kStages) == 0 && kSplits % 2 == 0, "issue loop: one trip = two splits = three ring rounds");
     static_assert(offBias % 16 == 0 && offHeadW % 16 == 0, "bias / head-weight staging must be 16-byte aligned");
     static_assert(sizeof(HeadScratch) % 16 == 0, "HeadScratch must keep 16-byte alignment");
     static_assert(kRingSlotBytes % 128 == 0, "ring slots must stay 128-byte aligned");
@@ -79,18 +84,16 @@ static_assert(sizeof(Misc) <= 144, "Misc slot");
 // operands are warp-uniform (they live in uniform registers), only the elected lane issues.  Each operand
 // descriptor is "base + immediate" in 16-byte units (lo word = start>>4 | LBO>>4 << 16, hi word constant; every
 // shared-memory address is below 2^18, so the 14-bit start field needs no masking).
-// K order of a trunk conv: channel half 0 for all nine taps, then half 1, so the MMAs of half 0 can start as
-// soon as the previous layer's epilogue has written channels [0, F/2).
-// Loop shape: one trip = one ring round = one tap row (3 taps = 3 ring slots, slot index == dx + 1), unrolled
-// inside, rolled outside.  Fully unrolled (144 MMAs) the issue code alone is 24 KB and fights the epilogue for
-// the instruction cache; fully rolled, the per-stage descriptor arithmetic lands on the issue critical path.
+// K order of a trunk conv: 32-channel split 0 for all nine taps, then split 1, ...: the MMAs over a split start
+// as soon as the previous layer's epilogue has written those 32 channels (bar_act[tile * kSplits + split]).
+// Loop shape: one trip = two splits = 18 stages = three ring rounds, unrolled inside (ring slots, tap shifts and
+// barrier phases are immediates), rolled outside.
 template <int F, bool STEM>
 __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off, uint32_t d_col, uint64_t* bar_full,
                                             uint64_t* bar_empty, uint64_t* bar_acc, uint64_t* bar_act, uint32_t act_phase,
                                             uint32_t& round)
 {
     using C = Cfg<F>;
-    static_assert(kStages == 3 && kStagesPerConv == 18, "one ring round = one tap row");
     constexpr uint32_t idesc = umma_idesc(F);
     constexpr uint32_t kAHi = (uint32_t)(kGroupUnits) | (1u << 14);                 // SBO = 144 B, version 1
     constexpr uint32_t kBHi = (uint32_t)(128 >> 4) | (1u << 14);                    // SBO = 128 B
@@ -102,23 +105,26 @@ __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off,
     const uint32_t a_row0 = (((smem_base + in_off) >> 4) + kGuardUnits + kHaloUnits) | kALboField;
     const uint32_t ring0 = ((smem_base + (uint32_t)C::offRing) >> 4) | kBLboField;
     if (STEM) {
-        mbar_wait(&bar_act[0], act_phase); mbar_wait(&bar_act[1], act_phase);
-        mbar_wait(&bar_act[2], act_phase); mbar_wait(&bar_act[3], act_phase);
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {                                               // stage s = tap row dy = s - 1, three taps
+        for (int i = 0; i < 2 * C::kSplits; ++i) mbar_wait(&bar_act[i], act_phase);
+#pragma unroll
+        for (int s = 0; s < 6; ++s) {                       // stage = (tap row dy = s/2 - 1, part): part 0 = taps dx -1,0; part 1 = dx +1
+            constexpr int kTapUnits = C::kStemTapBytes >> 4;
+            const int dy = s / 2, part = s % 2;
             mbar_wait(&bar_full[s], round & 1);
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
                 for (int tile = 0; tile < 2; ++tile) {
 #pragma unroll
-                    for (int t3 = 0; t3 < 3; ++t3) {
-                        const uint32_t a_u = a_row0 + (uint32_t)(tile * kTileUnits + (s - 1) * 2 * kGroupUnits + (t3 - 1));
-                        const uint32_t b_u = ring0 + (uint32_t)(s * kSlotUnits + t3 * 2 * F);
+                    for (int k = 0; k < (part == 0 ? 2 : 1); ++k) {
+                        const int tx = part == 0 ? k : 2;
+                        const uint32_t a_u = a_row0 + (uint32_t)(tile * kTileUnits + (dy - 1) * 2 * kGroupUnits + (tx - 1));
+                        const uint32_t b_u = ring0 + (uint32_t)(s * kSlotUnits + k * kTapUnits);
                         umma_bf16(d_col + (uint32_t)(tile * F), ((uint64_t)kAHi << 32) | a_u, ((uint64_t)kBHi << 32) | b_u, idesc,
-                                  (s > 0 || t3 > 0) ? 1u : 0u);
+                                  (s > 0 || k > 0) ? 1u : 0u);
                     }
-                    if (s == 2) umma_commit(&bar_acc[tile]);
+                    if (s == 5) umma_commit(&bar_acc[tile]);
                 }
                 umma_commit(&bar_empty[s]);
             }
@@ -127,34 +133,35 @@ __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off,
         ++round;
     } else {
 #pragma unroll 1
-        for (int r = 0; r < 6; ++r) {                                               // r = half * 3 + tap row
-            const int half = r >= 3 ? 1 : 0, ty = r - 3 * half;
-            if (ty == 0) {                                                          // first tap of a channel half
-                mbar_wait(&bar_act[0 + half], act_phase);                           // tile 0, this half
-                mbar_wait(&bar_act[2 + half], act_phase);                           // tile 1, this half
-            }
-            const uint32_t a_base = a_row0 + (uint32_t)(half * C::kPlanesPerHalf * kPlaneUnits + (ty - 1) * 2 * kGroupUnits - 1);
+        for (int trip = 0; trip < C::kSplits / 2; ++trip) {
+            const uint32_t a_trip = a_row0 + (uint32_t)(trip * 2 * C::kPlanesPerSplit * kPlaneUnits);
 #pragma unroll
-            for (int sl = 0; sl < 3; ++sl) {                                        // ring slot == tap column
-                mbar_wait(&bar_full[sl], round & 1);
+            for (int t = 0; t < 18; ++t) {
+                const int ql = t / 9, tap = t % 9, sl = t % kStages;
+                if (tap == 0) {                                                     // first tap of a channel split
+                    mbar_wait(&bar_act[0 * C::kSplits + trip * 2 + ql], act_phase); // tile 0
+                    mbar_wait(&bar_act[1 * C::kSplits + trip * 2 + ql], act_phase); // tile 1
+                }
+                mbar_wait(&bar_full[sl], (round + t / kStages) & 1);
                 tc_fence_after();
                 if (elect_one()) {
+                    const int shift = (tap / 3 - 1) * 2 * kGroupUnits + (tap % 3 - 1);
 #pragma unroll
                     for (int tile = 0; tile < 2; ++tile) {
 #pragma unroll
                         for (int j = 0; j < C::kMmasPerStage; ++j) {
-                            const uint32_t a_u = a_base + (uint32_t)(tile * kTileUnits + 2 * j * kPlaneUnits + sl);
+                            const uint32_t a_u = a_trip + (uint32_t)(tile * kTileUnits + (ql * C::kPlanesPerSplit + 2 * j) * kPlaneUnits + shift);
                             const uint32_t b_u = ring0 + (uint32_t)(sl * kSlotUnits + 2 * j * F);
                             umma_bf16(d_col + (uint32_t)(tile * F), ((uint64_t)kAHi << 32) | a_u, ((uint64_t)kBHi << 32) | b_u, idesc,
-                                      (sl > 0 || j > 0) ? 1u : (r > 0 ? 1u : 0u));
+                                      (t > 0 || j > 0) ? 1u : (trip > 0 ? 1u : 0u));
                         }
-                        if (sl == 2 && r == 5) umma_commit(&bar_acc[tile]);       // this tile's accumulator is complete
+                        if (t == 17 && trip == C::kSplits / 2 - 1) umma_commit(&bar_acc[tile]);   // this tile's accumulator is complete
                     }
                     umma_commit(&bar_empty[sl]);                                    // slot free once both tiles have read it
                 }
                 __syncwarp();
             }
-            ++round;
+            round += 3;
         }
     }
 }
@@ -171,6 +178,18 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
+}
+
+// tcgen05.wait::ld, tied to the registers of the load it completes so that no use can be scheduled above it
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
 }
 
 // 32 accumulator columns of one GEMM row -> +bias (+skip) -> ReLU -> bf16 -> four 16-byte stores.
@@ -341,7 +360,7 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
     uint64_t* bar_full = bars;                       // [kStages] weights landed
     uint64_t* bar_empty = bars + kStages;            // [kStages] slot consumed by the tensor core
     uint64_t* bar_acc = bars + 2 * kStages;          // [2] accumulator tile complete
-    uint64_t* bar_act = bars + 2 * kStages + 2;      // [tile*2 + half] activation half-tile written (128 arrivals)
+    uint64_t* bar_act = bars + 2 * kStages + 2;      // [tile*kSplits + split] 32 channels of the tile written (128 arrivals)
     float* head_w = reinterpret_cast<float*>(smem + C::offHeadW);
     Misc* misc = reinterpret_cast<Misc*>(smem + C::offMisc);
 
@@ -352,7 +371,7 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
         for (int i = 0; i < 2; ++i) mbar_init(&bar_acc[i], 1);
-        for (int i = 0; i < 4; ++i) mbar_init(&bar_act[i], 128);
+        for (int i = 0; i < 2 * C::kSplits; ++i) mbar_init(&bar_act[i], 128);
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < 3 * F; i += kThreads)
@@ -392,8 +411,8 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
             build_input_row(bufA, m, misc->s_self + 2 * tile, misc->s_opp + 2 * tile, misc->s_legal[it & 1] + 2 * tile);
             bufA[unit_of_row(1, m)] = make_uint4(0, 0, 0, 0);   // K padding plane of the stem
             fence_async_proxy();
-            mbar_arrive(&bar_act[tile * 2 + 0]);
-            mbar_arrive(&bar_act[tile * 2 + 1]);
+#pragma unroll
+            for (int q = 0; q < C::kSplits; ++q) mbar_arrive(&bar_act[tile * C::kSplits + q]);
             for (int layer = 0; layer < n_layers; ++layer, ++layer_count) {
                 const bool into_b = (layer == 0) || ((layer & 1) == 0);   // stem and conv2 write the residual stream
                 const bool skip = layer > 0 && (layer & 1) == 0;          // conv2: add the block input
@@ -412,29 +431,26 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
                 if (net.trace && blockIdx.x == 0 && tt == 0) net.trace[layer * 8 + 2 + 2 * tile] = clock64();
                 const uint32_t tcol = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((layer_count & 1) * 2 * F + tile * F);
                 float hp[3] = {0.f, 0.f, 0.f};
+                // 32 channels at a time: the load of the next split is in flight while this one is converted, and the next
+                // layer's MMAs over a split are released as soon as it is in shared memory
+                uint32_t r[2][32];
+                tmem_ld32_nowait(tcol, r[0]);
+                tmem_wait_ld(r[0]);
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    // channels [half*F/2, (half+1)*F/2): load them all, then convert; the next layer's MMAs over this
-                    // channel half are released as soon as it is in shared memory
-                    constexpr int kChunks = F / 64;            // 32-column chunks per half
-                    uint32_t r[kChunks][32];
-#pragma unroll
-                    for (int c = 0; c < kChunks; ++c) tmem_ld32_nowait(tcol + (uint32_t)((half * kChunks + c) * 32), r[c]);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int c = 0; c < kChunks; ++c) {
-                        if (last) {
-                            if (skip) epilogue_chunk<true, true>(r[c], half * kChunks + c, m, bias_s, bufB, out, head_w, F, hp);
-                            else epilogue_chunk<false, true>(r[c], half * kChunks + c, m, bias_s, bufB, out, head_w, F, hp);
-                        } else if (skip) epilogue_chunk<true, false>(r[c], half * kChunks + c, m, bias_s, bufB, out, head_w, F, hp);
-                        else epilogue_chunk<false, false>(r[c], half * kChunks + c, m, bias_s, bufB, out, head_w, F, hp);
-                    }
-                    tc_fence_before();
+                for (int q = 0; q < C::kSplits; ++q) {
+                    if (q + 1 < C::kSplits) tmem_ld32_nowait(tcol + (uint32_t)((q + 1) * 32), r[(q + 1) & 1]);
+                    if (last) {
+                        if (skip) epilogue_chunk<true, true>(r[q & 1], q, m, bias_s, bufB, out, head_w, F, hp);
+                        else epilogue_chunk<false, true>(r[q & 1], q, m, bias_s, bufB, out, head_w, F, hp);
+                    } else if (skip) epilogue_chunk<true, false>(r[q & 1], q, m, bias_s, bufB, out, head_w, F, hp);
+                    else epilogue_chunk<false, false>(r[q & 1], q, m, bias_s, bufB, out, head_w, F, hp);
                     if (!last) {
                         fence_async_proxy();                  // generic-proxy stores -> visible to the tensor core
-                        mbar_arrive(&bar_act[tile * 2 + half]);
+                        mbar_arrive(&bar_act[tile * C::kSplits + q]);
                     }
+                    if (q + 1 < C::kSplits) tmem_wait_ld(r[(q + 1) & 1]);
                 }
+                tc_fence_before();
                 if (last) {
                     // hand the 1x1-conv outputs (ReLU'd, flattened channel-major, net.py:90) to this tile's head warp
                     HeadScratch* hs = reinterpret_cast<HeadScratch*>(smem + C::offHeads) + tile;
@@ -456,9 +472,10 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
             for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const unsigned char* src = reinterpret_cast<const unsigned char*>(net.w_tc);
                 for (int layer = 0; layer < n_layers; ++layer) {
-                    const int stages = layer == 0 ? 3 : kStagesPerConv;
-                    const uint32_t bytes = layer == 0 ? C::kStemStageBytes : C::kStageBytes;
+                    const int stages = layer == 0 ? 6 : C::kStagesPerConv;
                     for (int s = 0; s < stages; ++s, ++cnt) {
+                        // stem stages alternate two taps / one tap (taps dx = -1,0 then dx = +1 of a tap row)
+                        const uint32_t bytes = layer == 0 ? ((s & 1) ? C::kStemTapBytes : 2 * C::kStemTapBytes) : C::kStageBytes;
                         const uint32_t slot = cnt % kStages, round = cnt / kStages;
                         mbar_wait(&bar_empty[slot], (round & 1) ^ 1);
                         mbar_expect_tx(&bar_full[slot], bytes);
