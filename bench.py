@@ -33,8 +33,24 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's banner / logs on stderr
+# stdout carries exactly one JSON line.  NCCL prints its version banner with printf on fd 1 (NCCL_DEBUG_FILE does not
+# catch it), so the real stdout is set aside here and fd 1 is pointed at stderr for everything else in the process.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_RESULT_OUT = None
+
+
+def isolate_stdout() -> None:
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 
 METRIC = "self-play games/s @50 sims/move 10x128 ResNet"
 UNIT = "games/s"
@@ -178,7 +194,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"each step: {sample}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -368,19 +384,20 @@ def run_b200(args):
         line["random_playout"]["cpu"] = cpu_playout_baseline()
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
 def main():
+    isolate_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--games", type=int, default=151552, help="concurrent games per GPU = games per step per GPU (1024 x 148 SMs)")
+    ap.add_argument("--games", type=int, default=303104, help="concurrent games per GPU = games per step per GPU (1024 x 148 SMs)")
     ap.add_argument("--sims", type=int, default=50)
     ap.add_argument("--blocks", type=int, default=10)
     ap.add_argument("--filters", type=int, default=128)

@@ -102,6 +102,7 @@ int oth_choose_greedy(oth_ctx* ctx, const uint64_t* self_b, const uint64_t* opp_
 /* ---- network: src/model/net.py OthelloResNet ------------------------------------ */
 #define OTH_NET_ENGINE_TCGEN05 0 /* bf16 tcgen05/TMEM implicit-GEMM trunk (product path) */
 #define OTH_NET_ENGINE_SIMT 1    /* CUDA-core validation kernel, same rounding points */
+#define OTH_NET_ENGINE_TCGEN05_PAIR 2 /* same trunk on CTA pairs (tcgen05 cta_group::2): half the weight traffic per SM */
 
 #define OTH_NET_OUT_LOGPROBS 0   /* log_softmax, what model(x) returns (net.py:94) */
 #define OTH_NET_OUT_PROBS 1      /* exp(log_softmax) as mcts.py:191 */

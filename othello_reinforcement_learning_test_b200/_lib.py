@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libothello_b200.so")
 
 OTH_OK = 0
 MEM_DEVICE, MEM_HOST = 0, 1
-ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
+ENGINE_TCGEN05, ENGINE_SIMT, ENGINE_TCGEN05_PAIR = 0, 1, 2
 OUT_LOGPROBS, OUT_PROBS, OUT_PRIORS = 0, 1, 2
 FLAG_ROOT_N_SUM, FLAG_Q_CANONICAL, FLAG_WINNER_BLACK, FLAG_EVAL_HASHNET, FLAG_EVAL_CACHE = 1, 2, 4, 8, 16
 FLAG_NO_SEARCH_SHARING = 32

@@ -65,7 +65,7 @@ int NetHost::load(const float* flat, int64_t count)
                 (long long)net_param_count(blocks, F));
     const int KC = F / 8, n_conv = 1 + 2 * blocks;
     const float* p = flat;
-    std::vector<uint16_t> wtc(w_tc_elems());
+    std::vector<uint16_t> wtc(w_tc_elems()), wtc2(w_tc_elems());
     std::vector<float> wsimt(w_simt_elems());
     std::vector<float> bias((size_t)n_conv * F);
     std::vector<float> scale, b;
@@ -95,6 +95,24 @@ int NetHost::load(const float* flat, int64_t count)
                         idx = ((((size_t)split * 9 + tap) * pps + pl) * F + co) * 8 + (ci % 8);
                     }
                     wtc[tc_off + idx] = h;
+                    // CTA-pair engine (net_tc2.cu): every ring stage is stored as [CTA 0's block][CTA 1's block], CTA r
+                    // holding cout rows [r*F/2, (r+1)*F/2).  Trunk stage = (split, tap): block [4 planes][F/2][8].
+                    // Stem stages per tap row dy: taps dx 0,1 (block [2 taps][2 planes][F/2][8]) then tap dx 2.
+                    {
+                        const int nhalf = F / 2, nh = co / nhalf, cr = co % nhalf;
+                        size_t idx2;
+                        if (conv == 0) {
+                            const int dy = tap / 3, dx = tap % 3, plane = ci / 8;
+                            const size_t tap_elems = (size_t)2 * nhalf * 8;
+                            const size_t stage_base = (size_t)dy * 6 * tap_elems + (dx < 2 ? 0 : 4 * tap_elems);
+                            const size_t in_block = (dx < 2 ? (size_t)dx : 0) * tap_elems + ((size_t)plane * nhalf + cr) * 8 + (ci % 8);
+                            idx2 = stage_base + (size_t)nh * (dx < 2 ? 2 : 1) * tap_elems + in_block;
+                        } else {
+                            const int pps = 4, plane = ci / 8, split = plane / pps, pl = plane % pps;
+                            idx2 = (((((size_t)split * 9 + tap) * 2 + nh) * pps + pl) * nhalf + cr) * 8 + (ci % 8);
+                        }
+                        wtc2[tc_off + idx2] = h;
+                    }
                     if (ci < cin_simt) wsimt[simt_off + ((size_t)tap * cin_simt + ci) * F + co] = bf16_to_f32(h);
                 }
         tc_off += (size_t)9 * cin_pad * F;
@@ -129,6 +147,7 @@ int NetHost::load(const float* flat, int64_t count)
     OTH_CHECK_CUDA(cudaSetDevice(ctx->device));
     auto up = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream); };
     OTH_CHECK_CUDA(up(d_w_tc, wtc.data(), wtc.size() * 2));
+    OTH_CHECK_CUDA(up(d_w_tc2, wtc2.data(), wtc2.size() * 2));
     OTH_CHECK_CUDA(up(d_w_simt, wsimt.data(), wsimt.size() * 4));
     float* f = d_small;
     auto put = [&](const std::vector<float>& v, const float** slot) {
@@ -145,7 +164,7 @@ int NetHost::load(const float* flat, int64_t count)
     OTH_CHECK_CUDA(put(v2_w, &dev.v2_w)); OTH_CHECK_CUDA(put(v2_b, &dev.v2_b));
     OTH_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
     dev.blocks = blocks; dev.F = F; dev.KC = KC;
-    dev.w_tc = (const __nv_bfloat16*)d_w_tc; dev.w_simt = d_w_simt;
+    dev.w_tc = (const __nv_bfloat16*)d_w_tc; dev.w_tc2 = (const __nv_bfloat16*)d_w_tc2; dev.w_simt = d_w_simt;
     loaded = true;
     return OTH_OK;
 }
@@ -154,6 +173,7 @@ int NetHost::allocate()
 {
     OTH_CHECK_CUDA(cudaSetDevice(ctx->device));
     OTH_CHECK_CUDA(cudaMalloc(&d_w_tc, w_tc_elems() * 2));
+    OTH_CHECK_CUDA(cudaMalloc(&d_w_tc2, w_tc_elems() * 2));
     OTH_CHECK_CUDA(cudaMalloc((void**)&d_w_simt, w_simt_elems() * 4));
     const size_t small = (size_t)(1 + 2 * blocks) * F + 2 * F + 2 + 128 * 65 + 65 + F + 1 + 64 * 256 + 256 + 256 + 1 + 64;
     OTH_CHECK_CUDA(cudaMalloc((void**)&d_small, small * 4));
@@ -163,8 +183,8 @@ int NetHost::allocate()
 void NetHost::release()
 {
     cudaSetDevice(ctx->device);
-    cudaFree(d_w_tc); cudaFree(d_w_simt); cudaFree(d_small);
-    d_w_tc = nullptr; d_w_simt = nullptr; d_small = nullptr;
+    cudaFree(d_w_tc); cudaFree(d_w_tc2); cudaFree(d_w_simt); cudaFree(d_small);
+    d_w_tc2 = nullptr; d_w_tc = nullptr; d_w_simt = nullptr; d_small = nullptr;
 }
 
 // ---- CUDA-core validation engine -----------------------------------------------------------
@@ -336,8 +356,9 @@ int oth_net_load_weights(oth_net* net, const float* flat, int64_t count)
 int oth_net_set_engine(oth_net* net, int engine)
 {
     OTH_REQUIRE(net, OTH_ERR_ARG, "oth_net_set_engine: net is NULL");
-    OTH_REQUIRE(engine == OTH_NET_ENGINE_TCGEN05 || engine == OTH_NET_ENGINE_SIMT, OTH_ERR_ARG, "unknown engine %d", engine);
-    OTH_REQUIRE(engine != OTH_NET_ENGINE_TCGEN05 || net_tc_supported(net->F), OTH_ERR_UNSUPPORTED,
+    OTH_REQUIRE(engine == OTH_NET_ENGINE_TCGEN05 || engine == OTH_NET_ENGINE_SIMT || engine == OTH_NET_ENGINE_TCGEN05_PAIR, OTH_ERR_ARG,
+                "unknown engine %d", engine);
+    OTH_REQUIRE(engine == OTH_NET_ENGINE_SIMT || net_tc_supported(net->F), OTH_ERR_UNSUPPORTED,
                 "tcgen05 engine supports num_filters 64 or 128 (got %d)", net->F);
     net->engine = engine;
     return OTH_OK;
@@ -397,6 +418,7 @@ int net_forward_device(NetHost* net, const uint64_t* self_b, const uint64_t* opp
 {
     TimedLaunch timed(net->ctx, 0);
     if (net->engine == OTH_NET_ENGINE_TCGEN05) return net_forward_tc(net, self_b, opp_b, n, policy, value, out_kind, n_dev);
+    if (net->engine == OTH_NET_ENGINE_TCGEN05_PAIR) return net_forward_tc2(net, self_b, opp_b, n, policy, value, out_kind, n_dev);
     return net_forward_simt(net, self_b, opp_b, n, policy, value, out_kind, n_dev);
 }
 }  // namespace oth

@@ -49,6 +49,7 @@ __host__ __device__ __forceinline__ int unit_of_row(int kc, int m)
 struct NetDev {
     int blocks, F, KC;
     const __nv_bfloat16* w_tc;   // UMMA B tiles: stem [9][2][F][8], then per conv [9][KC][F][8] (bf16, BN folded)
+    const __nv_bfloat16* w_tc2;  // the same tiles split by cout half for CTA pairs (net_tc2.cu): per stage [CTA 0's rows][CTA 1's rows]
     const float* w_simt;         // same weights widened to fp32: stem [9][8][F], then per conv [9][F(cin)][F(cout)]
     const float* bias;           // [1 + 2*blocks][F] folded BN bias
     const float* ph_w;           // [2][F]  policy 1x1 conv, BN folded (fp32)

@@ -11,6 +11,7 @@ struct NetHost {
     int engine = 0;
     bool loaded = false;
     void* d_w_tc = nullptr;
+    void* d_w_tc2 = nullptr;
     float* d_w_simt = nullptr;
     float* d_small = nullptr;
     NetDev dev{};
@@ -34,6 +35,8 @@ int net_forward_simt(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b
                      int out_kind, const int32_t* n_dev);
 int net_forward_tc(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value,
                    int out_kind, const int32_t* n_dev);
+int net_forward_tc2(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value,
+                    int out_kind, const int32_t* n_dev);
 
 }  // namespace oth
 

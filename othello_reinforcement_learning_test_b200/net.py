@@ -167,7 +167,7 @@ class InferenceNet:
         return net
 
     def set_engine(self, engine: str) -> None:
-        code = {"tcgen05": _lib.ENGINE_TCGEN05, "simt": _lib.ENGINE_SIMT}[engine]
+        code = {"tcgen05": _lib.ENGINE_TCGEN05, "simt": _lib.ENGINE_SIMT, "tcgen05_pair": _lib.ENGINE_TCGEN05_PAIR}[engine]
         check(self.ctx.lib.oth_net_set_engine(self.handle, code))
 
     def load_state_dict(self, sd) -> None:

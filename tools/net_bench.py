@@ -12,10 +12,11 @@ ap.add_argument("--n", type=int, default=148 * 4 * 32)
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--blocks", type=int, default=10)
 ap.add_argument("--filters", type=int, default=128)
+ap.add_argument("--engine", default=None, help="tcgen05 | tcgen05_pair | simt (default: the library's choice)")
 a = ap.parse_args()
 ctx = pkg.Context.default(0)
 torch.manual_seed(42)
-net = InferenceNet.from_module(OthelloResNet(a.blocks, a.filters).eval(), ctx)
+net = InferenceNet.from_module(OthelloResNet(a.blocks, a.filters).eval(), ctx, engine=a.engine)
 g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ref_games.npz"))
 live = np.flatnonzero(g["terminal"] == 0)
 idx = live[np.arange(a.n) % live.size]
@@ -32,5 +33,5 @@ e1.record(stream); e1.synchronize()
 ms = e0.elapsed_time(e1) / a.reps
 F, B = a.filters, a.blocks
 flop = 2 * (64 * 27 * F + B * 2 * 64 * 9 * F * F + 64 * 2 * F + 128 * 65 + 64 * F + 64 * 256 + 256)
-print(json.dumps({"kernel": "k_net_tc", "positions": a.n, "ms_per_launch": ms, "tflops": a.n * flop / ms / 1e9,
+print(json.dumps({"kernel": "k_net_tc", "engine": a.engine or "default", "positions": a.n, "ms_per_launch": ms, "tflops": a.n * flop / ms / 1e9,
                   "positions_per_s": a.n / ms * 1e3}))
