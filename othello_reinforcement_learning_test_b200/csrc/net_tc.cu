@@ -161,7 +161,7 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
     uint64_t* bar_full = bars;                       // [kStages] weights landed
     uint64_t* bar_empty = bars + kStages;            // [kStages] slot consumed by the tensor core
     uint64_t* bar_acc = bars + 2 * kStages;          // [2] accumulator tile complete
-    uint64_t* bar_act = bars + 2 * kStages + 2;      // [tile*kSplits + split] 32 channels of the tile written (128 arrivals)
+    uint64_t* bar_act = bars + 2 * kStages + 2;      // [tile*kSplits + split] 32 channels of the tile written (4 arrivals, one per warp)
     float* head_w = reinterpret_cast<float*>(smem + C::offHeadW);
     Misc* misc = reinterpret_cast<Misc*>(smem + C::offMisc);
 
@@ -172,7 +172,7 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
         for (int i = 0; i < 2; ++i) mbar_init(&bar_acc[i], 1);
-        for (int i = 0; i < 2 * C::kSplits; ++i) mbar_init(&bar_act[i], 128);
+        for (int i = 0; i < 2 * C::kSplits; ++i) mbar_init(&bar_act[i], 4);       // one arrival per epilogue warp of the tile
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < 3 * F; i += kThreads)
@@ -212,8 +212,11 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
             build_input_row(bufA, m, misc->s_self + 2 * tile, misc->s_opp + 2 * tile, misc->s_legal[it & 1] + 2 * tile);
             bufA[unit_of_row(1, m)] = make_uint4(0, 0, 0, 0);   // K padding plane of the stem
             fence_async_proxy();
+            __syncwarp();
+            if (lane == 0) {
 #pragma unroll
-            for (int q = 0; q < C::kSplits; ++q) mbar_arrive(&bar_act[tile * C::kSplits + q]);
+                for (int q = 0; q < C::kSplits; ++q) mbar_arrive(&bar_act[tile * C::kSplits + q]);
+            }
             for (int layer = 0; layer < n_layers; ++layer, ++layer_count) {
                 const bool into_b = (layer == 0) || ((layer & 1) == 0);   // stem and conv2 write the residual stream
                 const bool skip = layer > 0 && (layer & 1) == 0;          // conv2: add the block input
@@ -247,7 +250,8 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
                     else epilogue_chunk<false, false>(r[q & 1], q, m, bias_s, bufB, out, head_w, F, hp);
                     if (!last) {
                         fence_async_proxy();                  // generic-proxy stores -> visible to the tensor core
-                        mbar_arrive(&bar_act[tile * C::kSplits + q]);
+                        __syncwarp();                         // one arrival per warp: arrivals serialise on the barrier
+                        if (lane == 0) mbar_arrive(&bar_act[tile * C::kSplits + q]);
                     }
                     if (q + 1 < C::kSplits) tmem_wait_ld(r[(q + 1) & 1]);
                 }

@@ -14,8 +14,14 @@
 //   bar_full[slot]  leader: own expect_tx arrive + own bytes + the relay's remote arrive; peer: local only
 //   bar_empty[slot] tcgen05.commit multicast: one arrival in each CTA when the pair's MMAs have read the slot
 //   bar_acc[tile]   tcgen05.commit multicast: accumulators of the tile complete (each CTA reads its own TMEM)
-//   bar_act[..]     leader only: 128 local + 128 remote arrivals per (tile, 32-channel split)
+//   bar_act[..]     leader only: one arrival per epilogue warp of the tile, 4 local + 4 remote, per 32-channel split
 // Both CTAs of a pair walk the same number of items; an index past the end is a dummy item (zero boards, no stores).
+//
+// STATUS (measured on B200, 10x128, 18,944 positions/launch): bit-identical to net_tc.cu on every batch size tried, but
+// ~10 % slower kernel-only (1.46 vs 1.60-1.65 PFLOP/s): the pair's M=256 x N=128 x K=16 MMAs retire every ~78 cycles
+// instead of 64 (independent of ring depth 6/12 and of how the peer's "weights landed" reaches the leader), and the
+// network's N = F = 128 cannot be widened to hide it.  Kept as an opt-in engine (OTH_NET_ENGINE_TCGEN05_PAIR); the
+// single-CTA kernel stays the product path.
 //
 // Restates src/model/net.py:15-61,139-205 (eval mode, BN folded) -- numerics identical to net_tc.cu (bf16
 // operands, fp32 accumulation in TMEM, bf16 activations between layers, fp32 heads).
@@ -71,6 +77,7 @@ __device__ __forceinline__ void issue_layer2(uint32_t smem_base, uint32_t in_off
                                              uint32_t& round)
 {
     using C = Cfg2<F>;
+
     constexpr uint32_t idesc = umma_idesc_m256(F);
     constexpr uint32_t kAHi = (uint32_t)(kGroupUnits) | (1u << 14);                 // SBO = 144 B, version 1
     constexpr uint32_t kBHi = (uint32_t)(128 >> 4) | (1u << 14);                    // SBO = 128 B
@@ -170,7 +177,7 @@ k_net_tc2(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t*
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::kStages; ++i) { mbar_init(&bar_full[i], rank == 0 ? 2 : 1); mbar_init(&bar_empty[i], 1); }
         for (int i = 0; i < 2; ++i) mbar_init(&bar_acc[i], 1);
-        for (int i = 0; i < 2 * C::kSplits; ++i) mbar_init(&bar_act[i], 256);
+        for (int i = 0; i < 2 * C::kSplits; ++i) mbar_init(&bar_act[i], 8);     // one arrival per epilogue warp of the tile, both CTAs
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < 3 * F; i += kThreads)
@@ -213,8 +220,11 @@ k_net_tc2(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t*
             build_input_row(bufA, m, misc->s_self + 2 * tile, misc->s_opp + 2 * tile, misc->s_legal[it & 1] + 2 * tile);
             bufA[unit_of_row(1, m)] = make_uint4(0, 0, 0, 0);
             fence_async_proxy();
+            __syncwarp();
+            if (lane == 0) {
 #pragma unroll
-            for (int q = 0; q < C::kSplits; ++q) mbar_arrive_cluster(act0 + 8u * q);
+                for (int q = 0; q < C::kSplits; ++q) mbar_arrive_cluster(act0 + 8u * q);
+            }
             for (int layer = 0; layer < n_layers; ++layer, ++layer_count) {
                 const bool into_b = (layer == 0) || ((layer & 1) == 0);
                 const bool skip = layer > 0 && (layer & 1) == 0;
@@ -241,8 +251,9 @@ k_net_tc2(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t*
                     } else if (skip) epilogue_chunk<true, false>(r[q & 1], q, m, bias_s, bufB, out, head_w, F, hp);
                     else epilogue_chunk<false, false>(r[q & 1], q, m, bias_s, bufB, out, head_w, F, hp);
                     if (!last) {
-                        fence_async_proxy();
-                        mbar_arrive_cluster(act0 + 8u * q);
+                        fence_async_proxy();                  // generic-proxy stores -> visible to the tensor core
+                        __syncwarp();                         // one (remote) arrival per warp: arrivals serialise on the barrier
+                        if (lane == 0) mbar_arrive_cluster(act0 + 8u * q);
                     }
                     if (q + 1 < C::kSplits) tmem_wait_ld(r[(q + 1) & 1]);
                 }

@@ -91,3 +91,23 @@ def test_tc_engine_rejects_unsupported_filter_counts(ctx):
     net = InferenceNet(2, 32, ctx)                     # falls to the validation engine by itself
     with pytest.raises(pkg.OthelloB200Error):
         net.set_engine("tcgen05")
+
+
+@pytest.mark.parametrize("nb,nf", [(2, 64), (10, 128)])
+def test_pair_engine_is_bit_identical_to_the_single_cta_engine(ctx, golden_games, nb, nf):
+    """The CTA-pair trunk (tcgen05 cta_group::2, net_tc2.cu) computes the same sums in the same order: identical bits
+    for every output kind, for ragged batches (dummy items in the last round of a pair) and across launches."""
+    from othello_reinforcement_learning_test_b200.net import InferenceNet
+    sd = net_oracle.make_state_dict(nb, nf, 3)
+    one = InferenceNet(nb, nf, ctx, engine="tcgen05"); one.load_state_dict(sd)
+    two = InferenceNet(nb, nf, ctx, engine="tcgen05_pair"); two.load_state_dict(sd)
+    live = np.flatnonzero(golden_games["terminal"] == 0)
+    idx = np.random.default_rng(9).choice(live, 2371, replace=False)
+    S, O = golden_games["self_b"][idx], golden_games["opp_b"][idx]
+    for n in (1, 3, 4, 5, 9, 590, 593, 1185, 2371):                        # 1 CTA pair .. several rounds, odd item counts
+        for out in ("logprobs", "probs", "priors"):
+            a, av = one.forward(S[:n], O[:n], out=out)
+            b, bv = two.forward(S[:n], O[:n], out=out)
+            assert np.array_equal(a, b) and np.array_equal(av, bv), (n, out)
+    b2, bv2 = two.forward(S, O, out="priors")
+    assert np.array_equal(b, b2) and np.array_equal(bv, bv2)

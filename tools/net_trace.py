@@ -10,7 +10,7 @@ nb, nf = int(sys.argv[1]) if len(sys.argv) > 1 else 10, int(sys.argv[2]) if len(
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 592
 ctx = pkg.Context.default(0)
 torch.manual_seed(42)
-net = InferenceNet.from_module(OthelloResNet(nb, nf).eval(), ctx)
+net = InferenceNet.from_module(OthelloResNet(nb, nf).eval(), ctx, engine=(sys.argv[4] if len(sys.argv) > 4 else None))
 g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ref_games.npz"))
 S = np.ascontiguousarray(g["self_b"][:n]); O = np.ascontiguousarray(g["opp_b"][:n])
 L = 1 + 2 * nb
