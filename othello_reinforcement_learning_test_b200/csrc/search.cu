@@ -25,7 +25,7 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 
 __global__ void __launch_bounds__(kSearchBlock)
 k_tree_begin(TreeDev t, const uint64_t* __restrict__ self_b, const uint64_t* __restrict__ opp_b,
-             const uint8_t* __restrict__ active, int64_t n)
+             const uint8_t* __restrict__ active, int64_t n, int32_t* __restrict__ build_list)
 {
     const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (g >= t.games) return;
@@ -37,6 +37,7 @@ k_tree_begin(TreeDev t, const uint64_t* __restrict__ self_b, const uint64_t* __r
     t.pending[g] = 0; t.eval_slot[g] = -1;
     t.leaf_self[g] = 0ULL; t.leaf_opp[g] = 0ULL; t.leaf_legal[g] = 0ULL;
     if (g == 0) *t.batch_count = 0;
+    if (live && build_list) build_list[atomicAdd(t.act_count, 1)] = (int32_t)g;   // order is irrelevant: games are independent
 }
 
 __device__ __forceinline__ uint32_t cache_index(const TreeDev& t, uint64_t me, uint64_t you)
@@ -85,9 +86,10 @@ __global__ void __launch_bounds__(kSearchBlock) k_tree_root(TreeDev t, int64_t n
 __global__ void __launch_bounds__(kSearchBlock)
 k_tree_select(TreeDev t, int64_t n, float c32, uint32_t flags, uint32_t epoch, uint32_t gen)
 {
-    const int64_t g = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t i = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (g >= n) return;
+    if (i >= n) return;
+    const int64_t g = t.act_list ? (int64_t)t.act_list[i] : i;
     if (!t.active[g]) { if (lane == 0) t.pending[g] = 0; return; }
     Edge* E = t.edges + g * (int64_t)t.edge_cap;
     int32_t* path = t.path + g * t.path_cap;
@@ -155,8 +157,10 @@ k_tree_select(TreeDev t, int64_t n, float c32, uint32_t flags, uint32_t epoch, u
 // games with the same position share it, colliding positions get a slot of their own.
 __global__ void __launch_bounds__(kSearchBlock) k_tree_assign(TreeDev t, int64_t n)
 {
-    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (g >= n || !t.pending[g] || t.leaf_src[g] != kSrcMiss) return;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t g = t.act_list ? (int64_t)t.act_list[i] : i;
+    if (!t.pending[g] || t.leaf_src[g] != kSrcMiss) return;
     const uint32_t h = t.leaf_h[g];
     const uint32_t o = (uint32_t)(t.c_owner[h] & 0xFFFFFFFFULL);
     const uint64_t me = t.leaf_self[g], you = t.leaf_opp[g];
@@ -180,9 +184,11 @@ k_tree_expand(TreeDev t, int64_t n, const float* __restrict__ policy, const floa
 {
     __shared__ float s_pri[kWarpsPerBlock][68];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t g = blockIdx.x * (int64_t)kWarpsPerBlock + w;
+    const int64_t i = blockIdx.x * (int64_t)kWarpsPerBlock + w;
     if (blockIdx.x == 0 && threadIdx.x == 0) *t.batch_count = 0;      // the evaluator has consumed the batch
-    if (g >= n || !t.pending[g]) return;
+    if (i >= n) return;
+    const int64_t g = t.act_list ? (int64_t)t.act_list[i] : i;
+    if (!t.pending[g]) return;
     const uint64_t lg = t.leaf_legal[g];
     // where this leaf's evaluation is: the batch slot (own or shared), the table, or (external / hash-net) slot = game
     const uint8_t how = by_slot ? t.leaf_src[g] : kSrcSlot;
@@ -393,8 +399,10 @@ int SearchHost::allocate(oth_ctx* c, int64_t games, int sims)
     A(t.eval_policy, G * 65); A(t.eval_value, G);
     A(t.error_flag, 1);
     A(t.leaf_h, G); A(t.leaf_src, G); A(t.dedup_of, G); A(t.stats, 4);
+    A(act_list_buf, G); A(t.act_count, 1);
 #undef A
     t.cache_mask = 0;
+    t.act_list = nullptr;
     OTH_CHECK_CUDA(cudaMemsetAsync(t.stats, 0, 4 * sizeof(unsigned long long), c->stream));
     OTH_CHECK_CUDA(cudaMemsetAsync(t.leaf_src, 0, G, c->stream));
     OTH_CHECK_CUDA(cudaMemsetAsync(t.error_flag, 0, sizeof(int32_t), c->stream));
@@ -410,8 +418,8 @@ void SearchHost::release()
     allocs.clear();
 }
 
-static inline int warp_grid(int64_t n) { return (int)((n + kWarpsPerBlock - 1) / kWarpsPerBlock); }
-static inline int thread_grid(int64_t n) { return (int)((n + kSearchBlock - 1) / kSearchBlock); }
+static inline int warp_grid(int64_t n) { return n > 0 ? (int)((n + kWarpsPerBlock - 1) / kWarpsPerBlock) : 1; }
+static inline int thread_grid(int64_t n) { return n > 0 ? (int)((n + kSearchBlock - 1) / kSearchBlock) : 1; }
 
 #define K_CHECK()                                 \
     do {                                          \
@@ -424,8 +432,18 @@ int SearchHost::begin(const uint64_t* d_self, const uint64_t* d_opp, const uint8
     OTH_REQUIRE(n_games >= 0 && n_games <= max_games, OTH_ERR_ARG, "search: %lld games exceed the capacity %lld",
                 (long long)n_games, (long long)max_games);
     n = n_games;
-    k_tree_begin<<<thread_grid(max_games), kSearchBlock, 0, ctx->stream>>>(t, d_self, d_opp, d_active, n);
+    // with an activity mask (self-play: one search per group of identical roots) the searching games are compacted
+    const bool listed = d_active != nullptr;
+    if (listed) OTH_CHECK_CUDA(cudaMemsetAsync(t.act_count, 0, sizeof(int32_t), ctx->stream));
+    k_tree_begin<<<thread_grid(max_games), kSearchBlock, 0, ctx->stream>>>(t, d_self, d_opp, d_active, n, listed ? act_list_buf : nullptr);
     K_CHECK();
+    t.act_list = nullptr; n_act = n;
+    if (listed) {
+        int32_t cnt = 0;
+        OTH_CHECK_CUDA(cudaMemcpyAsync(&cnt, t.act_count, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        OTH_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        t.act_list = act_list_buf; n_act = cnt;
+    }
     begun = true; awaiting_apply = false; root_pending = true;
     return OTH_OK;
 }
@@ -451,7 +469,7 @@ int SearchHost::select(bool use_cache)
 {
     TimedLaunch timed(ctx, 1);
     ++epoch;
-    k_tree_select<<<warp_grid(n), kSearchBlock, 0, ctx->stream>>>(tree_view(t, use_cache), n, (float)c_puct, flags, epoch, generation);
+    k_tree_select<<<warp_grid(n_act), kSearchBlock, 0, ctx->stream>>>(tree_view(t, use_cache), n_act, (float)c_puct, flags, epoch, generation);
     K_CHECK();
     return OTH_OK;
 }
@@ -460,7 +478,7 @@ int SearchHost::assign()
 {
     if (!t.cache_mask) return OTH_OK;
     TimedLaunch timed(ctx, 1);
-    k_tree_assign<<<thread_grid(n), kSearchBlock, 0, ctx->stream>>>(t, n);
+    k_tree_assign<<<thread_grid(n_act), kSearchBlock, 0, ctx->stream>>>(t, n_act);
     K_CHECK();
     return OTH_OK;
 }
@@ -497,7 +515,7 @@ int SearchHost::read_stats(unsigned long long out[4], bool reset)
 int SearchHost::expand(const float* d_policy, const float* d_value, bool policy_is_raw, bool by_slot)
 {
     TimedLaunch timed(ctx, 1);
-    k_tree_expand<<<warp_grid(n), kSearchBlock, 0, ctx->stream>>>(t, n, d_policy, d_value, policy_is_raw ? 1 : 0, by_slot ? 1 : 0,
+    k_tree_expand<<<warp_grid(n_act), kSearchBlock, 0, ctx->stream>>>(t, n_act, d_policy, d_value, policy_is_raw ? 1 : 0, by_slot ? 1 : 0,
                                                                    epoch, generation);
     K_CHECK();
     return OTH_OK;

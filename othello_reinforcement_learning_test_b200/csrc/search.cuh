@@ -57,6 +57,10 @@ struct TreeDev {
     float* eval_policy;       // [games][65]
     float* eval_value;        // [games]
     int32_t* error_flag;      // != 0: a pool overflowed
+    // compact list of the games that really search this move (self-play shares searches among identical roots, so
+    // most slots idle): the per-simulation kernels walk it instead of all slots.  nullptr = every game (identity).
+    const int32_t* act_list;
+    int32_t* act_count;
 };
 
 constexpr uint8_t kSrcSlot = 0;      // own slot in the evaluation batch (cache off, or colliding entry: no insert)
@@ -68,6 +72,8 @@ constexpr uint8_t kSrcMiss = 4;      // (between select and assign) wants an eva
 struct SearchHost {
     oth_ctx* ctx = nullptr;
     int64_t max_games = 0, n = 0;
+    int64_t n_act = 0;                    // entries of t.act_list (== n when the list is off)
+    int32_t* act_list_buf = nullptr;
     int max_sims = 0;
     double c_puct = 1.0, dir_alpha = 0.3, dir_eps = 0.25;
     uint32_t flags = 0;
