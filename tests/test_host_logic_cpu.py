@@ -138,6 +138,16 @@ def test_dropin_routes_the_reference_import_paths():
         assert (w.num_simulations, w.temperature_threshold, w.num_parallel_games, w.batch_mcts.c_puct) == (50, 20, 16, 1.5)
         m = MCTS(None, "cpu", c_puct=1.5)
         assert (m.model, m.device, m.c_puct, m.dirichlet_alpha, m.dirichlet_epsilon) == (None, "cpu", 1.5, 0.3, 0.25)
+        # the rows SURVEY 8(f) marks "next" are opt-in: not routed by default ...
+        assert "src.train.buffer" not in sys.modules and "src.eval.arena" not in sys.modules
+        dropin.uninstall()
+        dropin.install(replay_buffer=True, arena=True)
+        from src.train.buffer import ReplayBuffer
+        from src.eval.arena import BatchArena, MatchResult, evaluate_player
+        from src.eval.players import RandomPlayer, GreedyPlayer, MCTSPlayer
+        assert ReplayBuffer is pkg.ReplayBuffer and BatchArena is pkg.BatchArena and MatchResult is pkg.MatchResult
+        assert RandomPlayer is pkg.RandomPlayer and GreedyPlayer is pkg.GreedyPlayer and MCTSPlayer is pkg.MCTSPlayer
+        assert evaluate_player is pkg.evaluate_player
     finally:
         dropin.uninstall()
         for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
