@@ -22,6 +22,9 @@ namespace oth {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kSearchBlock = kWarpsPerBlock * 32;
 constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int kLanesPerGame = 8;                       // k_tree_select / k_tree_expand: lanes that walk one game
+constexpr int kGamesPerWarp = 32 / kLanesPerGame;
+constexpr int kGamesPerBlock = kWarpsPerBlock * kGamesPerWarp;
 
 __global__ void __launch_bounds__(kSearchBlock)
 k_tree_begin(TreeDev t, const uint64_t* __restrict__ self_b, const uint64_t* __restrict__ opp_b,
@@ -83,61 +86,72 @@ __global__ void __launch_bounds__(kSearchBlock) k_tree_root(TreeDev t, int64_t n
     request_evaluation(t, g, a, b, epoch, gen);
 }
 
+// One descent per searching game.  A game is walked by a GROUP of 8 lanes (4 games per warp): a node has ~9 children
+// on average (26 at most in the observed trees), so 8 lanes score them in one or two trips, and four independent
+// pointer chases per warp hide each other's latency -- the kernel is bound by dependent 24-byte loads, not by lanes.
 __global__ void __launch_bounds__(kSearchBlock)
 k_tree_select(TreeDev t, int64_t n, float c32, uint32_t flags, uint32_t epoch, uint32_t gen)
 {
-    const int64_t i = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (i >= n) return;
-    const int64_t g = t.act_list ? (int64_t)t.act_list[i] : i;
-    if (!t.active[g]) { if (lane == 0) t.pending[g] = 0; return; }
+    const int lane = threadIdx.x & 31, sub = lane & (kLanesPerGame - 1);
+    const int64_t i = (blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5)) * kGamesPerWarp + (lane / kLanesPerGame);
+    bool live = i < n;
+    const int64_t g = live ? (t.act_list ? (int64_t)t.act_list[i] : i) : 0;
+    if (live && !t.active[g]) { if (sub == 0) t.pending[g] = 0; live = false; }
+    if (!__any_sync(kFull, live)) return;
     Edge* E = t.edges + g * (int64_t)t.edge_cap;
     int32_t* path = t.path + g * t.path_cap;
 
-    uint64_t me = t.root_self[g], you = t.root_opp[g];
-    int first = 0, cnt = t.root_count[g], depth = 0;
-    int parent_n = (flags & OTH_FLAG_ROOT_N_SUM) ? t.sims_done[g] : 0;   // mcts.py:152-172: the root is never updated
-    for (;;) {
+    uint64_t me = live ? t.root_self[g] : 0ULL, you = live ? t.root_opp[g] : 0ULL;
+    int first = 0, cnt = live ? t.root_count[g] : 0, depth = 0;
+    int parent_n = (live && (flags & OTH_FLAG_ROOT_N_SUM)) ? t.sims_done[g] : 0;   // mcts.py:152-172: the root is never updated
+    bool descending = live;
+    while (__any_sync(kFull, descending)) {
         const double root_of_n = sqrt((double)parent_n);
         double best = -INFINITY;
         int best_e = 0x7FFFFFFF, b_n = 0, b_first = kEdgeLeaf, b_cnt = 0, b_act = 0;
-        for (int k = lane; k < cnt; k += 32) {
-            const Edge ed = E[first + k];                                   // one 24-byte record per child
-            double q = ed.n ? ed.w / (double)ed.n : 0.0;                    // node.py:51-60
-            if (flags & OTH_FLAG_Q_CANONICAL) q = -q;
-            const float cp = __fmul_rn(c32, ed.p);                          // float32 product (weak Python scalar)
-            const double u = __ddiv_rn(__dmul_rn((double)cp, root_of_n), (double)(1 + ed.n));
-            const double s = __dadd_rn(q, u);
-            if (s > best) {                                                 // strict >: first maximum wins
-                best = s; best_e = first + k; b_n = ed.n; b_first = ed.child_first; b_cnt = ed.child_count; b_act = ed.action;
+        if (descending) {
+            for (int k = sub; k < cnt; k += kLanesPerGame) {
+                const Edge ed = E[first + k];                                   // one 24-byte record per child
+                double q = ed.n ? ed.w / (double)ed.n : 0.0;                    // node.py:51-60
+                if (flags & OTH_FLAG_Q_CANONICAL) q = -q;
+                const float cp = __fmul_rn(c32, ed.p);                          // float32 product (weak Python scalar)
+                const double u = __ddiv_rn(__dmul_rn((double)cp, root_of_n), (double)(1 + ed.n));
+                const double sc = __dadd_rn(q, u);
+                if (sc > best) {                                                // strict >: first maximum wins
+                    best = sc; best_e = first + k; b_n = ed.n; b_first = ed.child_first; b_cnt = ed.child_count; b_act = ed.action;
+                }
             }
         }
-        int win_lane = lane;
+        int win_lane = sub;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double os = __shfl_xor_sync(kFull, best, o);
-            const int oe = __shfl_xor_sync(kFull, best_e, o);
-            const int ol = __shfl_xor_sync(kFull, win_lane, o);
+        for (int o = kLanesPerGame / 2; o > 0; o >>= 1) {
+            const double os = __shfl_xor_sync(kFull, best, o, kLanesPerGame);
+            const int oe = __shfl_xor_sync(kFull, best_e, o, kLanesPerGame);
+            const int ol = __shfl_xor_sync(kFull, win_lane, o, kLanesPerGame);
             if (os > best || (os == best && oe < best_e)) { best = os; best_e = oe; win_lane = ol; }
         }
-        const int e = best_e;
-        parent_n = __shfl_sync(kFull, b_n, win_lane);
-        const int child_first = __shfl_sync(kFull, b_first, win_lane);
-        cnt = __shfl_sync(kFull, b_cnt, win_lane);
-        const int action = __shfl_sync(kFull, b_act, win_lane);
-        if (lane == 0) path[depth] = e;
-        ++depth;
-        apply_known_legal(me, you, action);                                 // mcts.py:122
-        if (cnt == 0 || depth >= t.path_cap) break;                         // child not expanded: this is the leaf
-        first = child_first;
+        const int w_n = __shfl_sync(kFull, b_n, win_lane, kLanesPerGame);
+        const int w_first = __shfl_sync(kFull, b_first, win_lane, kLanesPerGame);
+        const int w_cnt = __shfl_sync(kFull, b_cnt, win_lane, kLanesPerGame);
+        const int w_act = __shfl_sync(kFull, b_act, win_lane, kLanesPerGame);
+        if (descending) {
+            parent_n = w_n;
+            cnt = w_cnt;
+            if (sub == 0) path[depth] = best_e;
+            ++depth;
+            apply_known_legal(me, you, w_act);                                  // mcts.py:122
+            if (cnt == 0 || depth >= t.path_cap) descending = false;            // child not expanded: this is the leaf
+            else first = w_first;
+        }
     }
+    if (!live) return;
     const uint64_t lg = legal_moves(me, you);
     const bool terminal = lg == 0 && legal_moves(you, me) == 0;           // mcts.py:127
-    if (lane == 0) {
+    if (sub == 0) {
         if (terminal) {
             double v = (double)winner(me, you);                            // mcts.py:129-130
-            for (int i = depth - 1; i >= 0; --i) {                         // mcts.py:152-168
-                Edge* ed = E + path[i];
+            for (int d = depth - 1; d >= 0; --d) {                         // mcts.py:152-168
+                Edge* ed = E + path[d];
                 ed->n += 1;
                 ed->w += v;
                 v = -v;
@@ -177,46 +191,51 @@ __global__ void __launch_bounds__(kSearchBlock) k_tree_assign(TreeDev t, int64_t
     if (o != (uint32_t)g) atomicAdd(&t.stats[3], 1ULL);        // different position on the same entry
 }
 
-// Expand the pending leaf of every game with the evaluator's output and back the value up.
+// Expand the pending leaf of every game with the evaluator's output and back the value up (8 lanes per game).
 __global__ void __launch_bounds__(kSearchBlock)
 k_tree_expand(TreeDev t, int64_t n, const float* __restrict__ policy, const float* __restrict__ value, int policy_is_raw,
               int by_slot, uint32_t epoch, uint32_t gen)
 {
-    __shared__ float s_pri[kWarpsPerBlock][68];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t i = blockIdx.x * (int64_t)kWarpsPerBlock + w;
+    __shared__ float s_pri[kWarpsPerBlock * kGamesPerWarp][68];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & (kLanesPerGame - 1), grp = lane / kLanesPerGame;
+    const int64_t i = (blockIdx.x * (int64_t)kWarpsPerBlock + w) * kGamesPerWarp + grp;
     if (blockIdx.x == 0 && threadIdx.x == 0) *t.batch_count = 0;      // the evaluator has consumed the batch
-    if (i >= n) return;
-    const int64_t g = t.act_list ? (int64_t)t.act_list[i] : i;
-    if (!t.pending[g]) return;
-    const uint64_t lg = t.leaf_legal[g];
+    bool live = i < n;
+    const int64_t g = live ? (t.act_list ? (int64_t)t.act_list[i] : i) : 0;
+    if (live && !t.pending[g]) live = false;
+    if (!__any_sync(kFull, live)) return;
+    const uint64_t lg = live ? t.leaf_legal[g] : 0ULL;
     // where this leaf's evaluation is: the batch slot (own or shared), the table, or (external / hash-net) slot = game
-    const uint8_t how = by_slot ? t.leaf_src[g] : kSrcSlot;
+    const uint8_t how = (live && by_slot) ? t.leaf_src[g] : kSrcSlot;
     int64_t src = g;
-    if (by_slot) src = how == kSrcDedup ? (int64_t)t.eval_slot[t.dedup_of[g]] : (int64_t)t.eval_slot[g];
+    if (live && by_slot) src = how == kSrcDedup ? (int64_t)t.eval_slot[t.dedup_of[g]] : (int64_t)t.eval_slot[g];
     const float* prow = how == kSrcCache ? t.c_priors + (size_t)t.leaf_h[g] * 68 : policy + src * 65;
-    const float leaf_value = how == kSrcCache ? t.c_value[t.leaf_h[g]] : value[src];
-    float* pri = s_pri[w];
-    for (int j = lane; j < 65; j += 32) pri[j] = prow[j];
-    __syncwarp();
-    if (policy_is_raw && lane == 0) mask_and_renormalise(pri, lg);        // node.py:71-80
-    __syncwarp();
-    const int depth = t.path_len[g];
-    const int cnt = lg ? popc64(lg) : 1;                                   // [64] = forced pass (bitboard.pyx:176-178)
-    const int first = t.n_edges[g];
-    if (first + cnt > t.edge_cap) {
-        if (lane == 0) { atomicExch(t.error_flag, 1); t.pending[g] = 0; }
-        return;
+    float leaf_value = 0.f;
+    float* pri = s_pri[w * kGamesPerWarp + grp];
+    if (live) {
+        leaf_value = how == kSrcCache ? t.c_value[t.leaf_h[g]] : value[src];
+        for (int j = sub; j < 65; j += kLanesPerGame) pri[j] = prow[j];
     }
+    __syncwarp();
+    if (live && policy_is_raw && sub == 0) mask_and_renormalise(pri, lg);  // node.py:71-80
+    __syncwarp();
+    const int depth = live ? t.path_len[g] : 0;
+    const int cnt = lg ? popc64(lg) : 1;                                   // [64] = forced pass (bitboard.pyx:176-178)
+    const int first = live ? t.n_edges[g] : 0;
+    if (live && first + cnt > t.edge_cap) {
+        if (sub == 0) { atomicExch(t.error_flag, 1); t.pending[g] = 0; }
+        live = false;
+    }
+    if (!live) return;                                                     // no warp-wide synchronisation below
     Edge* E = t.edges + g * (int64_t)t.edge_cap;
-    for (int k = lane; k < cnt; k += 32) {
+    for (int k = sub; k < cnt; k += kLanesPerGame) {
         Edge ed;
         ed.w = 0.0; ed.n = 0; ed.child_first = kEdgeLeaf; ed.child_count = 0; ed.pad = 0;
         const int action = lg ? nth_set_bit(lg, k) : kPass;
         ed.p = pri[action]; ed.action = (uint8_t)action;
         E[first + k] = ed;
     }
-    if (lane == 0) {
+    if (sub == 0) {
         t.n_nodes[g] += 1;
         t.n_edges[g] = first + cnt;
         t.n_evals[g] += 1;
@@ -227,8 +246,8 @@ k_tree_expand(TreeDev t, int64_t n, const float* __restrict__ policy, const floa
             Edge* leaf = E + path[depth - 1];
             leaf->child_first = first; leaf->child_count = (uint8_t)cnt;
             double v = (double)leaf_value;                                 // value.item(), mcts.py:144
-            for (int i = depth - 1; i >= 0; --i) {
-                Edge* ed = E + path[i];
+            for (int d = depth - 1; d >= 0; --d) {
+                Edge* ed = E + path[d];
                 ed->n += 1;
                 ed->w += v;
                 v = -v;
@@ -242,8 +261,8 @@ k_tree_expand(TreeDev t, int64_t n, const float* __restrict__ policy, const floa
         const uint32_t h = t.leaf_h[g];
         if (t.c_hit_epoch[h] != epoch) {
             float* dst = t.c_priors + (size_t)h * 68;
-            for (int j = lane; j < 65; j += 32) dst[j] = pri[j];
-            if (lane == 0) {
+            for (int j = sub; j < 65; j += kLanesPerGame) dst[j] = pri[j];
+            if (sub == 0) {
                 t.c_key[h] = make_ulonglong2(t.leaf_self[g], t.leaf_opp[g]);
                 t.c_value[h] = leaf_value;
                 t.c_gen[h] = gen;
@@ -419,6 +438,7 @@ void SearchHost::release()
 }
 
 static inline int warp_grid(int64_t n) { return n > 0 ? (int)((n + kWarpsPerBlock - 1) / kWarpsPerBlock) : 1; }
+static inline int group_grid(int64_t n) { return n > 0 ? (int)((n + kGamesPerBlock - 1) / kGamesPerBlock) : 1; }
 static inline int thread_grid(int64_t n) { return n > 0 ? (int)((n + kSearchBlock - 1) / kSearchBlock) : 1; }
 
 #define K_CHECK()                                 \
@@ -469,7 +489,7 @@ int SearchHost::select(bool use_cache)
 {
     TimedLaunch timed(ctx, 1);
     ++epoch;
-    k_tree_select<<<warp_grid(n_act), kSearchBlock, 0, ctx->stream>>>(tree_view(t, use_cache), n_act, (float)c_puct, flags, epoch, generation);
+    k_tree_select<<<group_grid(n_act), kSearchBlock, 0, ctx->stream>>>(tree_view(t, use_cache), n_act, (float)c_puct, flags, epoch, generation);
     K_CHECK();
     return OTH_OK;
 }
@@ -515,7 +535,7 @@ int SearchHost::read_stats(unsigned long long out[4], bool reset)
 int SearchHost::expand(const float* d_policy, const float* d_value, bool policy_is_raw, bool by_slot)
 {
     TimedLaunch timed(ctx, 1);
-    k_tree_expand<<<warp_grid(n_act), kSearchBlock, 0, ctx->stream>>>(t, n_act, d_policy, d_value, policy_is_raw ? 1 : 0, by_slot ? 1 : 0,
+    k_tree_expand<<<group_grid(n_act), kSearchBlock, 0, ctx->stream>>>(t, n_act, d_policy, d_value, policy_is_raw ? 1 : 0, by_slot ? 1 : 0,
                                                                    epoch, generation);
     K_CHECK();
     return OTH_OK;
