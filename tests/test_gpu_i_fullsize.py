@@ -87,6 +87,23 @@ def test_baseline_sized_campaign_properties(ctx):
     assert a.tobytes() == b.tobytes()
 
 
+def test_strong_config_campaign_properties(ctx):
+    """BASELINE config 4 (strong_8x8.yaml:29-37): 100 simulations per move, c_puct 1.5, temperature threshold 20,
+    4096 concurrent games per GPU -- the same oracle-checked invariants as the default configuration."""
+    import othello_reinforcement_learning_test_b200 as pkg
+    from othello_reinforcement_learning_test_b200.net import OthelloResNet
+    torch.manual_seed(42)
+    model = OthelloResNet(10, 128).eval()
+    G = 4096
+    w = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, "cuda", num_simulations=100, c_puct=1.5, temperature_threshold=20,
+                                   num_parallel_games=16, concurrent_games=G, seed=5, verbose=False)
+    smp = w.execute_episodes_packed(G)
+    st = w.last_stats
+    assert 55 * G < smp.size < 70 * G
+    assert 5300 < st["nn_evals"] / G < 6000                                 # the reference measured 5,617 per game at 100 sims
+    _check_campaign(smp, 100, 20, G)
+
+
 def test_symmetry_augmentation_matches_board_symmetries(ctx):
     import othello_reinforcement_learning_test_b200 as pkg
     w = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", num_simulations=8, num_parallel_games=2, seed=2, verbose=False)

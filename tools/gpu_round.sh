@@ -8,10 +8,13 @@ timeout 1500 python -m pytest tests -q -m gpu -x --tb=short > "$OUT/pytest_gpu.l
 timeout 300 python __graft_entry__.py smoke > "$OUT/smoke.log" 2>&1; echo "smoke rc=$?" | tee -a "$OUT/summary.txt"
 timeout 900 python bench.py ${BENCH_ARGS:-} > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?" | tee -a "$OUT/summary.txt"
 if [ "${NCU:-1}" = "1" ]; then
-  NCU_CMD="python bench.py --steps 1 --warmup 0 --games 2368 --no-cpu-baseline"
-  timeout 600 $NCU_CMD > "$OUT/ncu_plain.log" 2>&1 && \
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file "$OUT/launches.csv" $NCU_CMD > "$OUT/ncu_launches.log" 2>&1
+  # launch list of the bench's own workload (default campaign size; one step, no warm-up: not a bench value), a window
+  # of 800 launches in the middle of the campaign -- kernel SHARES are comparable with roofline.kernel_share_of_step
+  LL_CMD="python bench.py --steps 1 --warmup 0 --no-cpu-baseline"
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 20000 -c 800 --csv --log-file "$OUT/launches.csv" $LL_CMD > "$OUT/ncu_launches.log" 2>&1
   echo "ncu launches rc=$?" | tee -a "$OUT/summary.txt"
+  NCU_CMD="python bench.py --steps 1 --warmup 0 --games 2368 --no-cpu-baseline"
+  timeout 600 $NCU_CMD > "$OUT/ncu_plain.log" 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_net_tc -s 400 -c 2 -o "$OUT/prof_net_tc" -f $NCU_CMD > "$OUT/ncu_full.log" 2>&1
   echo "ncu full rc=$?" | tee -a "$OUT/summary.txt"
   timeout 300 python tools/net_bench.py --n 18944 --reps 20 > "$OUT/net_bench.json" 2>&1 && \
