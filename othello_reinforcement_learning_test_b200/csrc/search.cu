@@ -1,10 +1,10 @@
-// search.cu -- GPU-resident Monte-Carlo tree search, one warp per game.
+// search.cu -- GPU-resident Monte-Carlo tree search, a group of 8 lanes per game (four games per warp).
 //
 // Restates src/mcts/node.py and src/mcts/mcts.py (and the lock-step BatchMCTS of
 // src/train/parallel_self_play.py:80-197) on a structure-of-arrays tree in HBM:
 //   select  (node.py:91-126, mcts.py:117-123): lanes score the children in parallel
 //           (float64 PUCT with a float32 c_puct*P product, exactly the promotion NumPy >= 2
-//           applies to `c_puct * child.prior * np.sqrt(N) / (1 + n)`), warp arg-max with the
+//           applies to `c_puct * child.prior * np.sqrt(N) / (1 + n)`), group arg-max with the
 //           reference's tie rule (first child in ascending action order);
 //   expand  (node.py:62-89): masked, renormalised priors in numpy's float32 summation order;
 //   backup  (mcts.py:152-168): sign flip per level, root never updated.
