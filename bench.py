@@ -292,7 +292,7 @@ def run_b200(args):
         if world > 1:
             h2d += 0 * odist.broadcast_weights(model, src=0)              # NCCL broadcast of the new weights
         net.sync_from(model, force=True)                                 # fold BN + bf16 pack + H2D
-        smp = worker.execute_episodes_packed(G, add_dirichlet_noise=True)   # campaign + D2H of this rank's packed samples
+        smp = worker.execute_episodes_packed(G, add_dirichlet_noise=True, reuse_buffer=True)   # campaign + D2H into pinned host memory
         if world > 1:                                                    # trajectories of every rank into the replay buffer,
             dptr, cnt = engine.samples_device()                          # NCCL all-gather device to device
             gathered, total_cnt = odist.all_gather_samples_device(dptr, cnt, torch.device("cuda", local))

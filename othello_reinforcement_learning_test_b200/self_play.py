@@ -64,7 +64,17 @@ class SelfPlayEngine:
         self.handle = h
         self.last_n_evals = 0
 
-    def run(self, net_handle, num_episodes: int) -> np.ndarray:
+    def _pinned_out(self, n: int) -> np.ndarray:
+        """Grow-only page-locked host buffer for the campaign's records (device->host at PCIe speed, no page faults)."""
+        import torch
+        need = max(int(n), 1) * _lib.SAMPLE_DTYPE.itemsize
+        buf = getattr(self, "_pinned", None)
+        if buf is None or buf.numel() < need:
+            self._pinned = buf = torch.empty(int(need * 1.1) + 4096, dtype=torch.uint8, pin_memory=True)
+        return buf.numpy()[:int(n) * _lib.SAMPLE_DTYPE.itemsize].view(_lib.SAMPLE_DTYPE)
+
+    def run(self, net_handle, num_episodes: int, reuse_buffer: bool = False) -> np.ndarray:
+        """reuse_buffer=True returns a view into the engine's pinned buffer, valid until the next run()."""
         ns, ne = C.c_int64(0), C.c_int64(0)
         check(self.ctx.lib.oth_selfplay_run(self.handle, net_handle, int(num_episodes), C.byref(ns), C.byref(ne)))
         self.last_n_evals = int(ne.value)
@@ -72,7 +82,7 @@ class SelfPlayEngine:
         check(self.ctx.lib.oth_selfplay_stats(self.handle, st))
         self.last_stats = {"nn_positions": int(st[0]), "cache_hits": int(st[1]), "same_step_duplicates": int(st[2]),
                            "hash_collisions": int(st[3]), "searches_run": int(st[4])}
-        out = np.empty(int(ns.value), _lib.SAMPLE_DTYPE)
+        out = self._pinned_out(int(ns.value)) if reuse_buffer else np.empty(int(ns.value), _lib.SAMPLE_DTYPE)
         check(self.ctx.lib.oth_selfplay_fetch(self.handle, ptr(out), out.size, MEM_HOST))
         return out
 
@@ -141,8 +151,9 @@ class ParallelSelfPlayWorker:
             self._engine_key = key
         return self._engine
 
-    def execute_episodes_packed(self, num_episodes: int, add_dirichlet_noise: bool = True) -> np.ndarray:
-        """Same campaign, packed records (structured array of oth_sample)."""
+    def execute_episodes_packed(self, num_episodes: int, add_dirichlet_noise: bool = True, reuse_buffer: bool = False) -> np.ndarray:
+        """Same campaign, packed records (structured array of oth_sample).  reuse_buffer=True: the result is a view
+        into a page-locked buffer owned by the worker (no 3 GB pageable allocation per campaign), valid until the next call."""
         m = self.batch_mcts
         if m.evaluator == "external":
             raise _lib.OthelloB200Error(
@@ -151,7 +162,7 @@ class ParallelSelfPlayWorker:
         t0 = time.time()
         eng = self._get_engine(num_episodes, add_dirichlet_noise)
         net = m._native_net().handle if m.evaluator == "native" else None
-        samples = eng.run(net, num_episodes)
+        samples = eng.run(net, num_episodes, reuse_buffer)
         dt = time.time() - t0
         self.last_stats = {"episodes": num_episodes, "samples": int(samples.size), "seconds": dt,
                            "nn_evals": eng.last_n_evals, "concurrent_games": eng.cfg.concurrent_games, **eng.last_stats}

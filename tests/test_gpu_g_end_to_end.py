@@ -103,3 +103,16 @@ def test_eval_cache_and_dedup_are_result_transparent(ctx, golden_games):
     st = m1._tree.stats()
     assert st["nn_positions"] + st["cache_hits"] + st["same_step_duplicates"] == int(e1.sum())
     assert st["cache_hits"] + st["same_step_duplicates"] > 0
+
+
+def test_packed_campaign_into_the_reusable_pinned_buffer(ctx):
+    """execute_episodes_packed(reuse_buffer=True) is the same records, delivered as a view into one page-locked buffer."""
+    import othello_reinforcement_learning_test_b200 as pkg
+    kw = dict(num_simulations=8, temperature_threshold=15, num_parallel_games=16, concurrent_games=96, seed=11, verbose=False)
+    fresh = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", **kw).execute_episodes_packed(96)
+    w = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", **kw)
+    view = w.execute_episodes_packed(96, reuse_buffer=True)
+    assert view.dtype == fresh.dtype and view.tobytes() == fresh.tobytes()
+    addr = view.__array_interface__["data"][0]
+    again = w.execute_episodes_packed(96, reuse_buffer=True)
+    assert again.__array_interface__["data"][0] == addr and again.size > 0          # same buffer, overwritten in place
