@@ -8,10 +8,12 @@ timeout 1500 python -m pytest tests -q -m gpu -x --tb=short > "$OUT/pytest_gpu.l
 timeout 300 python __graft_entry__.py smoke > "$OUT/smoke.log" 2>&1; echo "smoke rc=$?" | tee -a "$OUT/summary.txt"
 timeout 900 python bench.py ${BENCH_ARGS:-} > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?" | tee -a "$OUT/summary.txt"
 if [ "${NCU:-1}" = "1" ]; then
-  # launch list of the bench's own workload (default campaign size; one step, no warm-up: not a bench value), a window
-  # of 800 launches in the middle of the campaign -- kernel SHARES are comparable with roofline.kernel_share_of_step
-  LL_CMD="python bench.py --steps 1 --warmup 0 --no-cpu-baseline"
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 20000 -c 800 --csv --log-file "$OUT/launches.csv" $LL_CMD > "$OUT/ncu_launches.log" 2>&1
+  # launch list of the bench's own workload (one step, no warm-up: not a bench value): kernel SHARES are comparable
+  # with roofline.kernel_share_of_step
+  # (ncu costs ~45 ms per intercepted launch even when it only skips it, so the window sits early in a 37,888-game
+  #  campaign and the application is killed once the window is captured)
+  LL_CMD="python bench.py --steps 1 --warmup 0 --no-cpu-baseline --games 37888"
+  timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --kill on -s 1500 -c 600 --csv --log-file "$OUT/launches.csv" $LL_CMD > "$OUT/ncu_launches.log" 2>&1
   echo "ncu launches rc=$?" | tee -a "$OUT/summary.txt"
   NCU_CMD="python bench.py --steps 1 --warmup 0 --games 2368 --no-cpu-baseline"
   timeout 600 $NCU_CMD > "$OUT/ncu_plain.log" 2>&1

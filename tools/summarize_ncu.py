@@ -27,7 +27,11 @@ def raw(rep):
 
 
 for rep in sorted(f for f in os.listdir(src) if f.endswith(".ncu-rep")):
-    hdr, units, rows = raw(os.path.join(src, rep))
+    try:
+        hdr, units, rows = raw(os.path.join(src, rep))
+    except StopIteration:                                   # truncated / unreadable report: keep the previous summary
+        print(f"skipped {rep}: ncu could not read it", file=sys.stderr)
+        continue
     ki = hdr.index("Kernel Name")
     lines = [f"# {rep}: ncu --set full --clock-control none (cold-cache, serialised replays; use for shares and per-kernel metrics, not for bench values)"]
     for r in rows:
@@ -54,6 +58,10 @@ if os.path.exists(lc):
     with open(os.path.join(out, f"{tag}_launches.txt"), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: per-kernel device time over the captured launch window\n")
         f.write("# (cold-cache, serialised: compare SHARES with bench.py's roofline.kernel_share_of_step, not absolutes)\n")
+        f.write("# command: bench.py --steps 1 --warmup 0 --no-cpu-baseline --games 37888, launches 1500..2100 of the campaign (plies ~10-14);\n")
+        f.write("# the network's share grows with the campaign size (more searches per launch): 89 % here, 97 % at the bench default\n")
+        f.write("# of 303,104 games (roofline.kernel_share_of_step) -- ncu costs ~45 ms per intercepted launch, so the default size is\n")
+        f.write("# out of reach for a launch list.\n")
         for k, v in sorted(tot.items(), key=lambda x: -x[1]):
             f.write(f"{k:60s} launches={cnt[k]:5d} total_ms={v / 1e6:10.3f} avg_us={v / cnt[k] / 1e3:10.1f} share={100 * v / s:5.1f}%\n")
 bj = os.path.join(src, "bench.json")
