@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one self-play campaign: G concurrent games per GPU (default 151552 = 1024 x 148 SMs) started
+A "step" is one self-play campaign: G concurrent games per GPU (default 303104 = 2048 x 148 SMs) started
 from the initial position and played to completion with the device-resident engine
 (ParallelSelfPlayWorker / oth_selfplay_run): per ply one search of 1 + 50 leaf evaluations per game
 (select -> tcgen05 ResNet -> expand/backup), move choice, trajectory recording, labelling.
@@ -397,7 +397,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--games", type=int, default=303104, help="concurrent games per GPU = games per step per GPU (1024 x 148 SMs)")
+    ap.add_argument("--games", type=int, default=303104, help="concurrent games per GPU = games per step per GPU (2048 x 148 SMs)")
     ap.add_argument("--sims", type=int, default=50)
     ap.add_argument("--blocks", type=int, default=10)
     ap.add_argument("--filters", type=int, default=128)
