@@ -117,7 +117,7 @@ class ClockSampler:
 
 def cpu_arm(args, model_sd, budget_s: float, threads=None):
     from oracle import selfplay_port
-    return selfplay_port.measure_games_per_second(model_sd, num_simulations=args.sims, c_puct=1.0, temperature_threshold=15,
+    return selfplay_port.measure_games_per_second(model_sd, num_simulations=args.sims, c_puct=args.c_puct, temperature_threshold=args.temp_threshold,
                                                   num_parallel_games=16, time_budget_s=budget_s, threads=threads,
                                                   mean_plies_per_game=MEAN_PLIES, seed=1)
 
@@ -161,8 +161,8 @@ def build_model(args):
 
 
 def config_dict(args, world):
-    return {"workload": f"default_8x8 self-play: {args.blocks}x{args.filters} ResNet, {args.sims} sims/move, c_puct 1.0, "
-                        f"temperature threshold 15, Dirichlet noise on; one step = {args.games} concurrent games per GPU "
+    return {"workload": f"default_8x8 self-play: {args.blocks}x{args.filters} ResNet, {args.sims} sims/move, c_puct {args.c_puct:g}, "
+                        f"temperature threshold {args.temp_threshold}, Dirichlet noise on; one step = {args.games} concurrent games per GPU "
                         f"played from the start position to completion",
             "games_per_step_per_gpu": args.games, "sims_per_move": args.sims, "parallelism": f"games sharded over {world} GPU(s), no "
             "collective inside the move loop", "weights": "random init, torch.manual_seed(42)",
@@ -215,7 +215,7 @@ def run_b200(args):
     if world > 1:
         odist.broadcast_weights(model, src=0)
     worker = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, torch.device("cuda", local), num_simulations=args.sims,
-                                        temperature_threshold=15, num_parallel_games=16, c_puct=1.0, dirichlet_alpha=0.3,
+                                        temperature_threshold=args.temp_threshold, num_parallel_games=16, c_puct=args.c_puct, dirichlet_alpha=0.3,
                                         dirichlet_epsilon=0.25, concurrent_games=args.games, engine=args.engine,
                                         seed=1000 + rank, verbose=False, eval_cache=not args.no_eval_cache, ctx=ctx)
     G = args.games
@@ -399,9 +399,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--games", type=int, default=303104, help="concurrent games per GPU = games per step per GPU (2048 x 148 SMs)")
     ap.add_argument("--sims", type=int, default=50)
+    ap.add_argument("--c-puct", type=float, default=1.0, help="default_8x8.yaml: 1.0; strong_8x8.yaml: 1.5")
+    ap.add_argument("--temp-threshold", type=int, default=15, help="default_8x8.yaml: 15; strong_8x8.yaml: 20")
     ap.add_argument("--blocks", type=int, default=10)
     ap.add_argument("--filters", type=int, default=128)
-    ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "simt"])
+    ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "tcgen05_pair", "simt"])
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="time budget of the cpu_baseline sample")
     ap.add_argument("--cpu-step-seconds", type=float, default=8.0, help="--impl reference: time budget per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
