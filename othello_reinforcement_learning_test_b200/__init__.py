@@ -25,14 +25,14 @@ from .bitboard import BoardBatch, OthelloBitboard   # noqa: E402
 from .mcts import MCTS, BatchMCTS   # noqa: E402
 from .net import InferenceNet, OthelloResNet, create_model   # noqa: E402
 from .buffer import PrioritizedReplayBuffer, ReplayBuffer   # noqa: E402
-from .arena import BatchArena, GreedyPlayer, MatchResult, MCTSPlayer, RandomPlayer, evaluate_player   # noqa: E402
+from .arena import Arena, BatchArena, GreedyPlayer, MatchResult, MCTSPlayer, RandomPlayer, evaluate_player   # noqa: E402
 from .self_play import (ParallelSelfPlayWorker, SelfPlayWorker, augment_data_with_symmetries,   # noqa: E402
                         create_parallel_self_play_worker)
 
 __all__ = [
     "Context", "OthelloB200Error", "OthelloBitboard", "BoardBatch", "MCTS", "BatchMCTS", "OthelloResNet",
     "InferenceNet", "create_model", "SelfPlayWorker", "ParallelSelfPlayWorker", "create_parallel_self_play_worker",
-    "augment_data_with_symmetries", "ReplayBuffer", "PrioritizedReplayBuffer", "BatchArena", "MatchResult", "RandomPlayer",
+    "augment_data_with_symmetries", "ReplayBuffer", "PrioritizedReplayBuffer", "Arena", "BatchArena", "MatchResult", "RandomPlayer",
     "GreedyPlayer", "MCTSPlayer", "evaluate_player",
 ]
 __version__ = "0.1.0"

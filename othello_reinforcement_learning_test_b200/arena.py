@@ -94,6 +94,25 @@ class MCTSPlayer(BatchPlayer):
         self.name, self.model, self.device, self.num_simulations = name, model, device, num_simulations
         self.mcts = MCTS(model=model, device=device, c_puct=1.0, **mcts_kwargs)
 
+    @classmethod
+    def from_checkpoint(cls, checkpoint_path: str, device, num_simulations: int = 50):
+        """players.py:159-222: network shape read off the checkpoint's state_dict (filters from the stem's weight,
+        blocks from the highest `res_blocks.N`), falling back to its `config`, then to 10 x 128."""
+        import torch
+        from .net import OthelloResNet
+        checkpoint = torch.load(checkpoint_path, map_location="cpu")
+        config = checkpoint.get("config", {})
+        sd = checkpoint["model_state_dict"]
+        num_filters = sd["conv_block.conv.weight"].shape[0] if "conv_block.conv.weight" in sd else config.get("num_filters", 128)
+        num_blocks = max((int(k.split(".")[1]) + 1 for k in sd if k.startswith("res_blocks.")), default=0)
+        if num_blocks == 0:
+            num_blocks = config.get("num_blocks", 10)
+        print(f"Detected model config: blocks={num_blocks}, filters={num_filters}")
+        model = OthelloResNet(num_blocks=num_blocks, num_filters=num_filters)
+        model.load_state_dict(sd)
+        model.eval()
+        return cls(model=model, device=device, num_simulations=num_simulations, name=f"MCTS-AI-{num_simulations}sim")
+
     def get_actions(self, self_b, opp_b, move_count, game_ids):
         legal = bb.legal_moves(self_b, opp_b, self.mcts._context())
         if self.num_simulations < 1:                                   # mcts.py:278-279: first legal move
@@ -116,13 +135,41 @@ class BatchArena:
         self.verbose = verbose
         self.ctx = ctx or Context.default()
 
+    def play_game(self, player1: BatchPlayer, player2: BatchPlayer, starting_player: int = 1) -> MatchResult:
+        """arena.py:68-162: one game; starting_player = 1 (player1 moves first) or -1."""
+        result = self._play(player1, player2, np.array([1 if starting_player == 1 else -1]))[0]
+        if self.verbose:
+            print(f"\n{result}\n")
+        return result
+
     def play_matches(self, player1: BatchPlayer, player2: BatchPlayer, num_games: int = 10,
                      alternate_colors: bool = True) -> List[MatchResult]:
         """arena.py:164-202"""
         n = int(num_games)
+        starting = np.where((np.arange(n) % 2 == 0) | (not alternate_colors), 1, -1)        # arena.py:187-190
+        results = self._play(player1, player2, starting)
+        if self.verbose:
+            self._print_summary(results, player1.name, player2.name)
+        return results
+
+    def _print_summary(self, results: List[MatchResult], player1_name: str, player2_name: str) -> None:
+        """arena.py:204-233"""
+        total = len(results)
+        w1 = sum(1 for r in results if r.winner == 1); w2 = sum(1 for r in results if r.winner == -1)
+        print("\n" + "=" * 70 + "\nMatch Summary\n" + "=" * 70)
+        print(f"\nTotal Games: {total}")
+        print(f"{player1_name}: {w1} wins ({w1 / total * 100 if total else 0:.1f}%)")
+        print(f"{player2_name}: {w2} wins ({w2 / total * 100 if total else 0:.1f}%)")
+        print(f"Draws: {total - w1 - w2}")
+        print(f"\nAverage Moves: {sum(r.num_moves for r in results) / total if total else 0:.1f}")
+        print(f"Average Duration: {sum(r.duration for r in results) / total if total else 0:.2f}s")
+        print("=" * 70 + "\n")
+
+    def _play(self, player1: BatchPlayer, player2: BatchPlayer, starting: np.ndarray) -> List[MatchResult]:
+        """All games of `starting` (one entry per game: +1 = player1 moves first) in flight together."""
+        n = int(starting.size)
         t0 = time.time()
         player1.reset(); player2.reset()
-        starting = np.where((np.arange(n) % 2 == 0) | (not alternate_colors), 1, -1)        # arena.py:187-190
         s = np.full(n, bb.START_SELF, np.uint64); o = np.full(n, bb.START_OPP, np.uint64); mc = np.zeros(n, np.int32)
         to_move = starting.copy()                       # +1: player1 moves, -1: player2 moves (arena.py:91-100)
         live = np.ones(n, bool)
@@ -156,6 +203,9 @@ class BatchArena:
                 w, p1, p2 = -wc, white, black                           # arena.py:139-147
             results.append(MatchResult(player1.name, player2.name, w, p1, p2, int(mc[i]), dur))
         return results
+
+
+Arena = BatchArena      # the reference's class name (src/eval/arena.py:54)
 
 
 def evaluate_player(player: BatchPlayer, opponent: BatchPlayer, num_games: int = 10, verbose: bool = False) -> dict:

@@ -46,7 +46,7 @@ def _ensure_package(name: str) -> types.ModuleType:
 _OPTIONAL = {
     # the rows SURVEY.md 8(f) marks "next": opt in with install(replay_buffer=True, arena=True)
     "replay_buffer": {"src.train.buffer": ("othello_reinforcement_learning_test_b200.buffer", ["ReplayBuffer", "PrioritizedReplayBuffer"])},
-    "arena": {"src.eval.arena": ("othello_reinforcement_learning_test_b200.arena", ["MatchResult", "BatchArena", "evaluate_player"]),
+    "arena": {"src.eval.arena": ("othello_reinforcement_learning_test_b200.arena", ["MatchResult", "Arena", "BatchArena", "evaluate_player"]),
               "src.eval.players": ("othello_reinforcement_learning_test_b200.arena", ["RandomPlayer", "GreedyPlayer", "MCTSPlayer"])},
 }
 

@@ -109,3 +109,19 @@ def test_greedy_and_random_choices_against_the_oracle(golden_games):
     res = pkg.BatchArena().play_matches(pkg.MCTSPlayer(None, "cuda", num_simulations=5), pkg.RandomPlayer(seed=9), num_games=32)
     assert len(res) == 32 and all(r.player1_score + r.player2_score <= 64 and 9 <= r.num_moves <= 130 for r in res)
     assert len({(r.player1_score, r.num_moves) for r in res}) > 8     # the random opponent really varies
+
+
+def test_arena_play_game_is_one_game_of_a_match(ctx, capsys):
+    """Arena.play_game (arena.py:68-162): the single-game entry point agrees with play_matches for both colour assignments."""
+    import othello_reinforcement_learning_test_b200 as pkg
+    a, b = pkg.GreedyPlayer(name="A"), pkg.GreedyPlayer(name="B")          # deterministic players
+    arena = pkg.Arena(verbose=False)
+    pair = arena.play_matches(a, b, num_games=2, alternate_colors=True)     # game 0: A starts, game 1: B starts
+    for starting, want in ((1, pair[0]), (-1, pair[1])):
+        got = arena.play_game(a, b, starting_player=starting)
+        assert (got.winner, got.player1_score, got.player2_score, got.num_moves) == \
+               (want.winner, want.player1_score, want.player2_score, want.num_moves)
+        assert (got.player1_name, got.player2_name) == ("A", "B")
+    pkg.Arena(verbose=True).play_matches(a, b, num_games=2)
+    out = capsys.readouterr().out
+    assert "Match Summary" in out and "Total Games: 2" in out and "Average Moves:" in out

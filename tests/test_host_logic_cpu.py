@@ -143,7 +143,8 @@ def test_dropin_routes_the_reference_import_paths():
         dropin.uninstall()
         dropin.install(replay_buffer=True, arena=True)
         from src.train.buffer import ReplayBuffer
-        from src.eval.arena import BatchArena, MatchResult, evaluate_player
+        from src.eval.arena import Arena, BatchArena, MatchResult, evaluate_player
+        assert Arena is BatchArena and hasattr(Arena, "play_game") and hasattr(Arena, "play_matches")
         from src.eval.players import RandomPlayer, GreedyPlayer, MCTSPlayer
         assert ReplayBuffer is pkg.ReplayBuffer and BatchArena is pkg.BatchArena and MatchResult is pkg.MatchResult
         assert RandomPlayer is pkg.RandomPlayer and GreedyPlayer is pkg.GreedyPlayer and MCTSPlayer is pkg.MCTSPlayer
@@ -224,3 +225,18 @@ def test_pack_training_data_round_trips_exactly(golden_games):
     pol = counts / counts.sum(axis=1, keepdims=True, dtype=np.float32)
     for i, (s, p, v) in enumerate(data):
         assert np.array_equal(st[i], s) and np.array_equal(pol[i], p) and float(packed["value"][i]) == v
+
+
+def test_mcts_player_from_checkpoint_reads_the_network_shape(tmp_path, capsys):
+    """players.py:159-222: blocks / filters come from the checkpoint's state_dict; the weights are loaded into our module."""
+    import torch
+    import othello_reinforcement_learning_test_b200 as pkg
+    torch.manual_seed(3)
+    src = pkg.OthelloResNet(3, 64)
+    path = tmp_path / "ckpt.pt"
+    torch.save({"model_state_dict": src.state_dict(), "config": {"num_blocks": 99, "num_filters": 7}}, path)
+    player = pkg.MCTSPlayer.from_checkpoint(str(path), "cuda", num_simulations=25)
+    assert "blocks=3, filters=64" in capsys.readouterr().out
+    assert player.name == "MCTS-AI-25sim" and player.num_simulations == 25 and not player.model.training
+    got = player.model.state_dict()
+    assert all(torch.equal(got[k], v) for k, v in src.state_dict().items())
