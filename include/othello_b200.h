@@ -174,9 +174,20 @@ typedef struct {
     int32_t concurrent_games;       /* device-resident game slots (num_parallel_games) */
     double c_puct, dirichlet_alpha, dirichlet_epsilon;
     uint32_t flags;                 /* OTH_FLAG_* */
-    uint32_t reserved;
-    uint64_t seed;
+    uint32_t schedule;              /* OTH_SCHEDULE_* (0 = auto) */
+    uint64_t seed;                  /* move-sampling seed of the first campaign; later campaigns on the handle derive their own */
 } oth_selfplay_config;
+
+/* How a campaign is scheduled on the device; the records produced are identical.
+ *   LOCKSTEP: one search per ply for every slot, 1 + num_simulations network launches per ply
+ *             (BatchMCTS.search_batch, parallel_self_play.py:80-170); slots with identical roots share one search.
+ *   ASYNC:    run-until-miss -- every slot keeps simulating, moving and starting its next search while its leaves hit
+ *             the evaluation cache, and only stops when it needs the network: one launch per cache miss of the slowest
+ *             slot instead of one per simulation.  Needs OTH_FLAG_EVAL_CACHE to pay off.
+ *   AUTO:     ASYNC up to 32768 slots when the evaluation cache is on, LOCKSTEP otherwise. */
+#define OTH_SCHEDULE_AUTO 0u
+#define OTH_SCHEDULE_LOCKSTEP 1u
+#define OTH_SCHEDULE_ASYNC 2u
 
 /* one training sample, packed (expanded to (f32[3,8,8], f32[65], float) by the Python shim) */
 typedef struct {
@@ -199,6 +210,12 @@ int oth_selfplay_run(oth_selfplay* sp, oth_net* net, int64_t num_episodes, int64
 /* statistics of the last run (HOST uint64[5]): [0..3] as oth_search_stats, [4] = searches actually run (slots with
  * identical root positions share one) */
 int oth_selfplay_stats(oth_selfplay* sp, uint64_t* out5);
+/* timing of the last run (HOST double[4]): [0] device milliseconds between the first and the last kernel of the campaign
+ * (CUDA events on the context stream), [1] network launches (lock-steps / ticks), [2] OTH_SCHEDULE_* really used,
+ * [3] kernels launched */
+int oth_selfplay_timing(oth_selfplay* sp, double* out4);
+/* new move-sampling seed for the next campaign on this handle (no re-allocation) */
+int oth_selfplay_set_seed(oth_selfplay* sp, uint64_t seed);
 /* copy the samples of the last run into a caller buffer (HOST or DEVICE) */
 int oth_selfplay_fetch(oth_selfplay* sp, oth_sample* out, int64_t capacity, int mem);
 /* device pointer + count of the last run's samples (for NCCL all-gather without a host hop) */

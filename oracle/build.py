@@ -7,7 +7,15 @@ Builds the two CPU checkers:
   compiled from the source where it lies under /root/reference (never copied
   into this repo; only the compiled module lands in the git-ignored
   ``oracle/_ref/``).  Skipped when /root/reference is absent (GPU box): the
-  prebuilt file travels with the snapshot.
+  prebuilt file travels with the snapshot;
+* ``oracle/_ref/src/**/*.pyc`` -- the REFERENCE'S OWN Python hot-path modules and
+  their callers (MCTS, network, self-play workers, replay buffer, trainer, arena,
+  players), byte-compiled with ``py_compile`` from the sources where they lie
+  (sourceless ``.pyc`` next to the compiled bitboard: outputs only, no reference
+  source text enters the repository or its history).  They let the GPU box run
+  the unmodified reference: as the CPU arm of bench.py (``--impl reference``) and
+  as the caller side of the drop-in tests (reference arena / self-play / trainer
+  code driving this package's classes).
 
 Only tests/, __graft_entry__ (build + smoke) and bench.py's cpu_baseline /
 ``--impl reference`` legs may import this module.
@@ -89,9 +97,47 @@ def build_ref(force: bool = False) -> str | None:
     return target
 
 
+# the reference's Python modules on and around the hot path; package __init__ files
+# included so that `import src.train.trainer` resolves exactly as it does in the reference tree
+REF_PY_MODULES = [
+    "src/__init__.py", "src/cython/__init__.py",
+    "src/mcts/__init__.py", "src/mcts/node.py", "src/mcts/mcts.py",
+    "src/model/__init__.py", "src/model/net.py",
+    "src/train/__init__.py", "src/train/self_play.py", "src/train/parallel_self_play.py", "src/train/buffer.py",
+    "src/train/trainer.py",
+    "src/eval/__init__.py", "src/eval/arena.py", "src/eval/players.py",
+    "benchmark.py",
+]
+
+
+def ref_python_root() -> str | None:
+    """Directory to put on sys.path so that `import src.mcts.mcts` finds the byte-compiled reference."""
+    return REF_OUT if os.path.exists(os.path.join(REF_OUT, "src", "mcts", "mcts.pyc")) else None
+
+
+def build_ref_python(force: bool = False) -> str | None:
+    """Byte-compile the reference's Python modules into oracle/_ref (sourceless .pyc, outputs only)."""
+    if not os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "mcts")):
+        return ref_python_root()            # GPU box: use what travelled
+    import py_compile
+    for rel in REF_PY_MODULES:
+        src = os.path.join(REFERENCE_ROOT, rel)
+        dst = os.path.join(REF_OUT, rel[:-3] + ".pyc")
+        if not os.path.exists(src):
+            raise RuntimeError(f"reference module {rel} not found under {REFERENCE_ROOT}")
+        if not force and os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(src):
+            continue
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        # dfile = the path shown in tracebacks; UNCHECKED_HASH: the .pyc must load without its source
+        py_compile.compile(src, cfile=dst, dfile=f"<reference>/{rel}", doraise=True,
+                           invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+    return ref_python_root()
+
+
 def main() -> None:
     print("oracle:", build_oracle(force="--force" in sys.argv))
     print("oracle/_ref:", build_ref(force="--force" in sys.argv))
+    print("oracle/_ref (python):", build_ref_python(force="--force" in sys.argv))
 
 
 if __name__ == "__main__":

@@ -6,9 +6,12 @@ Loads the REFERENCE ITSELF for pinning the oracle:
   from ``oracle/_ref`` (built by ``oracle/build.py``; travels to the GPU box as a
   prebuilt .so), imported under its own module name ``src.cython.bitboard``.
 * ``reference_python()`` -- the reference's pure-Python modules (MCTS, network,
-  batched self-play) imported straight from /root/reference.  Only available in
-  the build container; used by ``oracle/gen_golden.py`` to write the fixtures in
-  ``tests/golden/``.  Nothing that runs on the GPU box calls it.
+  batched self-play, trainer, arena, players), unmodified: imported straight from
+  /root/reference in the build container (``oracle/gen_golden.py`` writes the
+  fixtures in ``tests/golden/`` with them), or from the sourceless byte-code that
+  ``oracle/build.py`` compiled into ``oracle/_ref`` (``bytecode=True``; the only
+  form that exists on the GPU box, where it is bench.py's ``--impl reference`` arm
+  and the caller side of the drop-in tests).
 """
 from __future__ import annotations
 
@@ -43,22 +46,47 @@ def ref_bitboard_class():
     return mod.OthelloBitboard
 
 
-def reference_available() -> bool:
+def reference_sources_available() -> bool:
     return os.path.isdir(os.path.join(_build.REFERENCE_ROOT, "src", "mcts"))
 
 
-def reference_python():
-    """Import the reference's Python hot-path modules from /root/reference.
+def reference_available() -> bool:
+    """True when the reference's Python can be imported here: sources (build container) or byte-code (anywhere)."""
+    return reference_sources_available() or _build.build_ref_python() is not None
+
+
+def reference_root(bytecode: bool | None = None) -> str:
+    """sys.path entry under which the reference's `src` package lives.  bytecode=None: sources if present."""
+    if bytecode is None:
+        bytecode = not reference_sources_available()
+    if not bytecode:
+        if not reference_sources_available():
+            raise RuntimeError("reference sources not present (build container only); use bytecode=True")
+        return _build.REFERENCE_ROOT
+    root = _build.build_ref_python()
+    if root is None:
+        raise RuntimeError("oracle/_ref holds no byte-compiled reference (run `python -m oracle.build` in the build container)")
+    return root
+
+
+def purge_reference_modules(keep_bitboard: bool = True) -> None:
+    """Forget every imported `src.*` module (reference or drop-in shim) so the next import resolves afresh."""
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        if keep_bitboard and k == "src.cython.bitboard":
+            continue
+        del sys.modules[k]
+
+
+def reference_python(bytecode: bool | None = None):
+    """Import the reference's Python hot-path modules (unmodified) from /root/reference or from oracle/_ref.
 
     Returns a namespace with MCTS, MCTSNode, BatchMCTS, ParallelSelfPlayWorker,
-    SelfPlayWorker, OthelloResNet, OthelloBitboard.  Build-container only.
+    SelfPlayWorker, OthelloResNet, OthelloBitboard, ReplayBuffer, Arena, players, AlphaZeroTrainer.
     """
-    if not reference_available():
-        raise RuntimeError("reference sources not present (this only works in the build container)")
     Board = ref_bitboard_class()
     if Board is None:
         raise RuntimeError("oracle/_ref is not built")
-    root = _build.REFERENCE_ROOT
+    root = reference_root(bytecode)
     # make the real 'src' package resolvable while keeping the compiled bitboard we just loaded
     bb = sys.modules["src.cython.bitboard"]
     for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
@@ -84,4 +112,5 @@ def reference_python():
     players = importlib.import_module("src.eval.players")
     ns.Arena, ns.evaluate_player = arena.Arena, arena.evaluate_player
     ns.GreedyPlayer, ns.RandomPlayer, ns.MCTSPlayer = players.GreedyPlayer, players.RandomPlayer, players.MCTSPlayer
+    ns.root = root
     return ns

@@ -21,6 +21,7 @@ ENGINE_TCGEN05, ENGINE_SIMT, ENGINE_TCGEN05_PAIR = 0, 1, 2
 OUT_LOGPROBS, OUT_PROBS, OUT_PRIORS = 0, 1, 2
 FLAG_ROOT_N_SUM, FLAG_Q_CANONICAL, FLAG_WINNER_BLACK, FLAG_EVAL_HASHNET, FLAG_EVAL_CACHE = 1, 2, 4, 8, 16
 FLAG_NO_SEARCH_SHARING = 32
+SCHEDULE_AUTO, SCHEDULE_LOCKSTEP, SCHEDULE_ASYNC = 0, 1, 2
 ACTIONS = 65
 
 
@@ -33,7 +34,7 @@ class SelfPlayConfig(C.Structure):
         ("num_simulations", C.c_int32), ("temperature_threshold", C.c_int32),
         ("add_dirichlet_noise", C.c_int32), ("concurrent_games", C.c_int32),
         ("c_puct", C.c_double), ("dirichlet_alpha", C.c_double), ("dirichlet_epsilon", C.c_double),
-        ("flags", C.c_uint32), ("reserved", C.c_uint32), ("seed", C.c_uint64),
+        ("flags", C.c_uint32), ("schedule", C.c_uint32), ("seed", C.c_uint64),
     ]
 
 
@@ -93,6 +94,8 @@ _PROTOS = {
     "oth_search_stats": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
     "oth_search_invalidate_cache": (C.c_int, [_p]),
     "oth_selfplay_stats": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
+    "oth_selfplay_timing": (C.c_int, [_p, C.POINTER(C.c_double)]),
+    "oth_selfplay_set_seed": (C.c_int, [_p, C.c_uint64]),
     "oth_selfplay_create": (C.c_int, [_p, C.POINTER(SelfPlayConfig), C.POINTER(_p)]),
     "oth_selfplay_destroy": (C.c_int, [_p]),
     "oth_selfplay_run": (C.c_int, [_p, _p, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
@@ -218,6 +221,47 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class torch_order:
+    """Orders a library call that takes torch CUDA tensors with torch's own stream.
+
+    The library works on its context stream (created non-blocking), torch on its current stream: without this the
+    kernel could read inputs torch has not produced yet, and torch could consume -- or its caching allocator could
+    recycle -- outputs the kernel has not written yet.  On entry the context stream waits for an event recorded on
+    torch's current stream; on exit the current stream waits for the context stream and every tensor is marked as
+    used by the context stream (`record_stream`).  No host synchronisation.  A no-op for host arrays, and when
+    torch's current stream IS the context stream (bench.py runs that way)."""
+
+    def __init__(self, ctx: "Context", *tensors):
+        self.ctx = ctx
+        self.tensors = [t for t in tensors if hasattr(t, "is_cuda") and t.is_cuda]
+
+    def __enter__(self):
+        self.ext = None
+        if not self.tensors:
+            return self
+        import torch
+        dev = self.tensors[0].device
+        cur = torch.cuda.current_stream(dev)
+        if cur.cuda_stream == self.ctx.stream:
+            return self
+        self.cur, self.ext = cur, torch.cuda.ExternalStream(self.ctx.stream, device=dev)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.ext.wait_event(ev)
+        return self
+
+    def __exit__(self, *exc):
+        if self.ext is None:
+            return False
+        import torch
+        ev = torch.cuda.Event()
+        ev.record(self.ext)
+        self.cur.wait_event(ev)
+        for t in self.tensors:
+            t.record_stream(self.ext)
+        return False
 
 
 def device_index(device) -> int:

@@ -64,7 +64,8 @@ def legal_moves(self_b, opp_b, ctx: Context | None = None):
     import torch  # noqa: F401  (only needed for device tensors)
     out = _like(s, np.uint64, s.shape, getattr(s, "dtype", None))
     n = int(np.prod(s.shape))
-    check(ctx.lib.oth_legal_moves(ctx.handle, ptr(s), ptr(o), ptr(out), n, _mem_of(s, o)))
+    with _lib.torch_order(ctx, s, o, out):
+        check(ctx.lib.oth_legal_moves(ctx.handle, ptr(s), ptr(o), ptr(out), n, _mem_of(s, o)))
     return out
 
 
@@ -74,7 +75,8 @@ def flips(self_b, opp_b, pos, ctx: Context | None = None):
     s, o = _u64(self_b), _u64(opp_b)
     p = np.ascontiguousarray(pos, np.int32) if not hasattr(pos, "is_cuda") else pos.contiguous()
     out = _like(s, np.uint64, s.shape, getattr(s, "dtype", None))
-    check(ctx.lib.oth_flips(ctx.handle, ptr(s), ptr(o), ptr(p), ptr(out), int(np.prod(s.shape)), _mem_of(s, o, p)))
+    with _lib.torch_order(ctx, s, o, p, out):
+        check(ctx.lib.oth_flips(ctx.handle, ptr(s), ptr(o), ptr(p), ptr(out), int(np.prod(s.shape)), _mem_of(s, o, p)))
     return out
 
 
@@ -90,7 +92,8 @@ def make_move(self_b, opp_b, move_count, action, ctx: Context | None = None):
     else:
         import torch
         ok = torch.empty(n, dtype=torch.uint8, device=self_b.device)
-    check(ctx.lib.oth_make_move(ctx.handle, ptr(self_b), ptr(opp_b), ptr(move_count), ptr(action), ptr(ok), n, mem))
+    with _lib.torch_order(ctx, self_b, opp_b, move_count, action, ok):
+        check(ctx.lib.oth_make_move(ctx.handle, ptr(self_b), ptr(opp_b), ptr(move_count), ptr(action), ptr(ok), n, mem))
     return ok
 
 
@@ -106,7 +109,8 @@ def terminal_winner(self_b, opp_b, ctx: Context | None = None):
         import torch
         t = torch.empty(n, dtype=torch.uint8, device=s.device); w = torch.empty(n, dtype=torch.int8, device=s.device)
         c = torch.empty((n, 2), dtype=torch.int32, device=s.device)
-    check(ctx.lib.oth_terminal_winner(ctx.handle, ptr(s), ptr(o), ptr(t), ptr(w), ptr(c), n, mem))
+    with _lib.torch_order(ctx, s, o, t, w, c):
+        check(ctx.lib.oth_terminal_winner(ctx.handle, ptr(s), ptr(o), ptr(t), ptr(w), ptr(c), n, mem))
     return t, w, c
 
 
@@ -121,7 +125,8 @@ def tensor_input(self_b, opp_b, ctx: Context | None = None):
     else:
         import torch
         out = torch.empty((n, 3, 8, 8), dtype=torch.float32, device=s.device)
-    check(ctx.lib.oth_tensor_input(ctx.handle, ptr(s), ptr(o), ptr(out), n, mem))
+    with _lib.torch_order(ctx, s, o, out):
+        check(ctx.lib.oth_tensor_input(ctx.handle, ptr(s), ptr(o), ptr(out), n, mem))
     return out
 
 

@@ -85,6 +85,13 @@ class ReplayBuffer:
             check(self.ctx.lib.oth_replay_add(self.handle, dev_ptr, n, MEM_DEVICE))
         return n
 
+    def add_device(self, records, count: int) -> None:
+        """Append `count` packed records held in a CUDA uint8 tensor (e.g. dist.all_gather_samples_device's result);
+        the copy into the ring is ordered after whatever torch stream produced the tensor."""
+        if count:
+            with _lib.torch_order(self.ctx, records):
+                check(self.ctx.lib.oth_replay_add(self.handle, ptr(records), int(count), MEM_DEVICE))
+
     # ---- sampling ---------------------------------------------------------------------------------
     def _draw(self, batch_size: int) -> np.ndarray:
         n = len(self)
@@ -108,9 +115,8 @@ class ReplayBuffer:
         st = torch.empty((batch_size, 3, 8, 8), dtype=torch.float32, device=dev)
         po = torch.empty((batch_size, 65), dtype=torch.float32, device=dev)
         va = torch.empty((batch_size, 1), dtype=torch.float32, device=dev)
-        torch.cuda.current_stream(dev).synchronize()
-        check(self.ctx.lib.oth_replay_gather(self.handle, ptr(idx), batch_size, ptr(st), ptr(po), ptr(va), MEM_DEVICE))
-        self.ctx.sync()
+        with _lib.torch_order(self.ctx, idx, st, po, va):     # ordered with torch's stream on the device, no host sync
+            check(self.ctx.lib.oth_replay_gather(self.handle, ptr(idx), batch_size, ptr(st), ptr(po), ptr(va), MEM_DEVICE))
         return st, po, va
 
     # ---- bookkeeping --------------------------------------------------------------------------------

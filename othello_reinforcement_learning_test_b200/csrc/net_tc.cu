@@ -71,7 +71,7 @@ struct Cfg {
 // as soon as the previous layer's epilogue has written those 32 channels (bar_act[tile * kSplits + split]).
 // Loop shape: one trip = two splits = 18 stages = three ring rounds, unrolled inside (ring slots, tap shifts and
 // barrier phases are immediates), rolled outside.
-template <int F, bool STEM>
+template <int F, bool STEM, int TILES>
 __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off, uint32_t d_col, uint64_t* bar_full,
                                             uint64_t* bar_empty, uint64_t* bar_acc, uint64_t* bar_act, uint32_t act_phase,
                                             uint32_t& round)
@@ -89,7 +89,7 @@ __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off,
     const uint32_t ring0 = ((smem_base + (uint32_t)C::offRing) >> 4) | kBLboField;
     if (STEM) {
 #pragma unroll
-        for (int i = 0; i < 2 * C::kSplits; ++i) mbar_wait(&bar_act[i], act_phase);
+        for (int i = 0; i < TILES * C::kSplits; ++i) mbar_wait(&bar_act[i], act_phase);
 #pragma unroll
         for (int s = 0; s < 6; ++s) {                       // stage = (tap row dy = s/2 - 1, part): part 0 = taps dx -1,0; part 1 = dx +1
             constexpr int kTapUnits = C::kStemTapBytes >> 4;
@@ -98,7 +98,7 @@ __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off,
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
-                for (int tile = 0; tile < 2; ++tile) {
+                for (int tile = 0; tile < TILES; ++tile) {
 #pragma unroll
                     for (int k = 0; k < (part == 0 ? 2 : 1); ++k) {
                         const int tx = part == 0 ? k : 2;
@@ -123,14 +123,14 @@ __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off,
                 const int ql = t / 9, tap = t % 9, sl = t % kStages;
                 if (tap == 0) {                                                     // first tap of a channel split
                     mbar_wait(&bar_act[0 * C::kSplits + trip * 2 + ql], act_phase); // tile 0
-                    mbar_wait(&bar_act[1 * C::kSplits + trip * 2 + ql], act_phase); // tile 1
+                    if (TILES > 1) mbar_wait(&bar_act[1 * C::kSplits + trip * 2 + ql], act_phase); // tile 1
                 }
                 mbar_wait(&bar_full[sl], (round + t / kStages) & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     const int shift = (tap / 3 - 1) * 2 * kGroupUnits + (tap % 3 - 1);
 #pragma unroll
-                    for (int tile = 0; tile < 2; ++tile) {
+                    for (int tile = 0; tile < TILES; ++tile) {
 #pragma unroll
                         for (int j = 0; j < C::kMmasPerStage; ++j) {
                             const uint32_t a_u = a_trip + (uint32_t)(tile * kTileUnits + (ql * C::kPlanesPerSplit + 2 * j) * kPlaneUnits + shift);
@@ -149,7 +149,10 @@ __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off,
     }
 }
 
-template <int F>
+// TILES = 2: the throughput shape (4 boards per item, every weight stage feeds two tiles).  TILES = 1: the latency shape
+// for small batches (2 boards per item, twice as many CTAs busy, half the MMAs per layer on each): what a tick of a
+// 100-game campaign needs.  Same instructions per board in the same order, so outputs are identical bit for bit.
+template <int F, int TILES>
 __global__ void __launch_bounds__(kThreads, 1)
 k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* __restrict__ opp_b, int64_t n,
          float* __restrict__ policy_out, float* __restrict__ value_out, int out_kind, const int32_t* __restrict__ n_dev)
@@ -167,7 +170,8 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_layers = 1 + 2 * net.blocks;
-    const int64_t n_items = (n + 3) / 4;
+    constexpr int kItemBoards = 2 * TILES;
+    const int64_t n_items = (n + kItemBoards - 1) / kItemBoards;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
@@ -188,7 +192,7 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
     tc_fence_after();
     const uint32_t tmem_base = misc->tmem_base;
 
-    if (warp < kComputeWarps) {
+    if (warp < kComputeWarps && (warp >> 2) < TILES) {
         // ===================== epilogue / input / heads =====================
         const int tile = warp >> 2;
         const int m = ((warp & 3) << 5) | lane;          // GEMM row == TMEM lane
@@ -202,13 +206,13 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
         uint32_t it = 0;                                  // items done by this CTA
         const float ph_b0 = __ldg(net.ph_b), ph_b1 = __ldg(net.ph_b + 1), vh_b = __ldg(net.vh_b);
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-            named_bar_sync(kBarAll, kComputeWarps * 32);        // everybody is done reading the previous item's misc->s_self/opp
-            if (threadIdx.x < 4) {
-                const int64_t b = item * 4 + threadIdx.x;
+            named_bar_sync(kBarAll, TILES * 128);               // everybody is done reading the previous item's misc->s_self/opp
+            if (threadIdx.x < kItemBoards) {
+                const int64_t b = item * kItemBoards + threadIdx.x;
                 const uint64_t a = b < n ? self_b[b] : 0ULL, o = b < n ? opp_b[b] : 0ULL;
                 misc->s_self[threadIdx.x] = a; misc->s_opp[threadIdx.x] = o; misc->s_legal[it & 1][threadIdx.x] = legal_moves(a, o);
             }
-            named_bar_sync(kBarAll, kComputeWarps * 32);
+            named_bar_sync(kBarAll, TILES * 128);
             build_input_row(bufA, m, misc->s_self + 2 * tile, misc->s_opp + 2 * tile, misc->s_legal[it & 1] + 2 * tile);
             bufA[unit_of_row(1, m)] = make_uint4(0, 0, 0, 0);   // K padding plane of the stem
             fence_async_proxy();
@@ -269,6 +273,8 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
                 if (net.trace && blockIdx.x == 0 && tt == 0) net.trace[layer * 8 + 3 + 2 * tile] = clock64();
             }
         }
+    } else if (warp < kComputeWarps) {
+        // tile 1's epilogue warps have nothing to do in the one-tile shape
     } else if (warp == kComputeWarps) {
         // ===================== weight producer =====================
         if (lane == 0) {
@@ -291,6 +297,8 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
             }
         }
         __syncwarp();
+    } else if (warp >= kHeadWarp0 + TILES) {
+        // no second tile, no second head warp
     } else if (warp >= kHeadWarp0) {
         // ===================== head warps =====================
         const int tile = warp - kHeadWarp0;
@@ -300,7 +308,7 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
         named_bar_arrive(kBarHeadFree + tile, 160);                           // the scratch starts out free
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             named_bar_sync(kBarHeadFull + tile, 160);
-            heads_tail_warp(net, hs, misc->s_legal[it & 1] + 2 * tile, item * 4 + 2 * tile, n, policy_out, value_out, out_kind, lane);
+            heads_tail_warp(net, hs, misc->s_legal[it & 1] + 2 * tile, item * kItemBoards + 2 * tile, n, policy_out, value_out, out_kind, lane);
             __syncwarp();
             if (item + gridDim.x < n_items) named_bar_arrive(kBarHeadFree + tile, 160);
         }
@@ -317,8 +325,8 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
                 const uint32_t in_off = from_a ? (uint32_t)C::offA : (uint32_t)C::offB;
                 const uint32_t d_col = tmem_u + (layer_count & 1) * 2 * F;  // accumulator buffer of this layer
                 if (net.trace && blockIdx.x == 0 && lane == 0) net.trace[layer * 8 + 0] = clock64();
-                if (layer == 0) issue_layer<F, true>(smem_base, in_off, d_col, bar_full, bar_empty, bar_acc, bar_act, act_phase, round);
-                else issue_layer<F, false>(smem_base, in_off, d_col, bar_full, bar_empty, bar_acc, bar_act, act_phase, round);
+                if (layer == 0) issue_layer<F, true, TILES>(smem_base, in_off, d_col, bar_full, bar_empty, bar_acc, bar_act, act_phase, round);
+                else issue_layer<F, false, TILES>(smem_base, in_off, d_col, bar_full, bar_empty, bar_acc, bar_act, act_phase, round);
                 act_phase ^= 1;
                 if (net.trace && blockIdx.x == 0 && lane == 0) net.trace[layer * 8 + 1] = clock64();
             }
@@ -337,23 +345,34 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
 
 bool net_tc_supported(int F) { return F == 64 || F == 128; }
 
+template <int F, int TILES>
+static int launch_tc(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value, int out_kind,
+                     const int32_t* n_dev)
+{
+    using C = tc::Cfg<F>;
+    oth_ctx* ctx = net->ctx;
+    const int64_t items = (n + 2 * TILES - 1) / (2 * TILES);
+    int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
+    if (grid < 1) grid = 1;
+    OTH_CHECK_CUDA(cudaFuncSetAttribute(tc::k_net_tc<F, TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    tc::k_net_tc<F, TILES><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(net->dev, self_b, opp_b, n, policy, value, out_kind, n_dev);
+    return OTH_OK;
+}
+
 int net_forward_tc(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value,
                    int out_kind, const int32_t* n_dev)
 {
     oth_ctx* ctx = net->ctx;
     OTH_REQUIRE(net_tc_supported(net->F), OTH_ERR_UNSUPPORTED, "tcgen05 engine supports num_filters 64 or 128 (got %d)", net->F);
-    const int64_t items = (n + 3) / 4;
-    int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
-    if (grid < 1) grid = 1;
-    if (net->F == 128) {
-        using C = tc::Cfg<128>;
-        OTH_CHECK_CUDA(cudaFuncSetAttribute(tc::k_net_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-        tc::k_net_tc<128><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(net->dev, self_b, opp_b, n, policy, value, out_kind, n_dev);
-    } else {
-        using C = tc::Cfg<64>;
-        OTH_CHECK_CUDA(cudaFuncSetAttribute(tc::k_net_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-        tc::k_net_tc<64><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(net->dev, self_b, opp_b, n, policy, value, out_kind, n_dev);
-    }
+    // `n` is the host's upper bound of the batch (the device count n_dev can only be smaller): when even that bound fits one
+    // two-board item per SM, the one-tile shape halves the per-layer latency; otherwise the two-tile shape is the faster one.
+    const bool one_tile = (n + 1) / 2 <= ctx->sm_count;
+    int rc;
+    if (net->F == 128) rc = one_tile ? launch_tc<128, 1>(net, self_b, opp_b, n, policy, value, out_kind, n_dev)
+                                     : launch_tc<128, 2>(net, self_b, opp_b, n, policy, value, out_kind, n_dev);
+    else rc = one_tile ? launch_tc<64, 1>(net, self_b, opp_b, n, policy, value, out_kind, n_dev)
+                       : launch_tc<64, 2>(net, self_b, opp_b, n, policy, value, out_kind, n_dev);
+    if (rc) return rc;
     ctx->launches++;
     OTH_CHECK_CUDA(cudaGetLastError());
     return OTH_OK;

@@ -43,11 +43,6 @@ k_tree_begin(TreeDev t, const uint64_t* __restrict__ self_b, const uint64_t* __r
     if (live && build_list) build_list[atomicAdd(t.act_count, 1)] = (int32_t)g;   // order is irrelevant: games are independent
 }
 
-__device__ __forceinline__ uint32_t cache_index(const TreeDev& t, uint64_t me, uint64_t you)
-{
-    return (uint32_t)(mix64(me ^ mix64(you + 0x9FB21C651E98DF25ULL)) & t.cache_mask);
-}
-
 // A pending leaf asks for its evaluation: table hit, or a request that k_tree_assign resolves, or (cache off)
 // a slot in the compacted batch right away.  Called by one thread per game.
 __device__ __forceinline__ void request_evaluation(const TreeDev& t, int64_t g, uint64_t me, uint64_t you, uint32_t epoch,

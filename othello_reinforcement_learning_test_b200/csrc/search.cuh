@@ -1,6 +1,7 @@
 // search.cuh -- device-resident SoA Monte-Carlo tree, shared by search.cu and selfplay.cu.
 #pragma once
 #include "common.cuh"
+#include "bitboard.cuh"
 #include "net_host.cuh"
 
 namespace oth {
@@ -62,6 +63,12 @@ struct TreeDev {
     const int32_t* act_list;
     int32_t* act_count;
 };
+
+// table index of a position in the evaluation cache
+__device__ __forceinline__ uint32_t cache_index(const TreeDev& t, uint64_t me, uint64_t you)
+{
+    return (uint32_t)(mix64(me ^ mix64(you + 0x9FB21C651E98DF25ULL)) & t.cache_mask);
+}
 
 constexpr uint8_t kSrcSlot = 0;      // own slot in the evaluation batch (cache off, or colliding entry: no insert)
 constexpr uint8_t kSrcOwner = 1;     // own slot, and inserts the result into the table

@@ -9,31 +9,9 @@
 // default, OTH_FLAG_WINNER_BLACK gives the black-relative label).  Unlike the reference a finished
 // slot is refilled with the next episode immediately instead of idling until the slowest game of
 // its batch ends.  Boards, trees, trajectories and labels never leave the GPU until fetched.
-#include "bitboard.cuh"
-#include "search.cuh"
+#include "selfplay.cuh"
 
 namespace oth {
-
-constexpr int kMaxPlies = 128;   // <= 60 placements + at most one pass between/around them
-static_assert(sizeof(oth_sample) == 168, "oth_sample layout is part of the C ABI");
-
-struct SelfPlayDev {
-    int64_t slots;
-    uint64_t *self_b, *opp_b;
-    int32_t *move_count, *game_id;
-    uint8_t* active;
-    oth_sample* staging;            // [slots][kMaxPlies]
-    oth_sample* out;
-    int64_t out_cap;
-    unsigned long long* counters;   // 0 started, 1 finished, 2 samples, 3 plies, 4 evals, 5 overflow, 6 searches run
-    // search-level sharing: slots whose root position is identical run ONE search (the search is a deterministic
-    // function of the root position), the others read the leader's root statistics
-    int32_t* leader;                // [slots] slot whose tree holds this slot's search
-    uint8_t* search_active;         // [slots] 1 = this slot runs a search this ply
-    uint32_t* root_h;               // [slots] index into the election table
-    unsigned long long* r_owner;    // [r_mask+1] (~ply << 32 | slot), atomicMin elects the leader
-    uint64_t r_mask;
-};
 
 __global__ void k_sp_reset(SelfPlayDev d, int64_t num_episodes)
 {
@@ -111,7 +89,7 @@ k_sp_move(SelfPlayDev d, TreeDev t, int64_t num_episodes, int threshold, uint64_
     // ---- choose the move (:379-382)
     int pick = best_k;
     if (ply < threshold && total > 0) {
-        const uint64_t r = mix64(seed ^ mix64(((uint64_t)(uint32_t)game << 16) ^ (uint64_t)ply));
+        const uint64_t r = move_draw(seed, game, ply);
         int target = (int)(((r >> 32) * (uint64_t)total) >> 32);   // uniform in [0,total)
         pick = cnt - 1;
         for (int k = 0; k < cnt; ++k) {
@@ -165,24 +143,6 @@ k_sp_move(SelfPlayDev d, TreeDev t, int64_t num_episodes, int threshold, uint64_
     }
 }
 
-struct SelfPlayHost {
-    oth_ctx* ctx = nullptr;
-    oth_selfplay_config cfg{};
-    SearchHost search;
-    SelfPlayDev d{};
-    std::vector<void*> allocs;
-    unsigned long long* h_counters = nullptr;   // pinned
-    int64_t last_samples = 0;
-    uint64_t moves_played = 0;
-    uint32_t ply_epoch = 0;
-    uint64_t last_searches = 0;
-    unsigned long long last_stats[4] = {0, 0, 0, 0};
-
-    int create(oth_ctx* c, const oth_selfplay_config* cf);
-    void release();
-    int run(NetHost* net, int64_t num_episodes, int64_t* n_samples, int64_t* n_evals);
-};
-
 int SelfPlayHost::create(oth_ctx* c, const oth_selfplay_config* cf)
 {
     ctx = c; cfg = *cf;
@@ -220,7 +180,12 @@ int SelfPlayHost::create(oth_ctx* c, const oth_selfplay_config* cf)
     if ((rc = grab((void**)&d.r_owner, rcap * sizeof(unsigned long long)))) return rc;
     OTH_CHECK_CUDA(cudaMemsetAsync(d.r_owner, 0xFF, rcap * sizeof(unsigned long long), c->stream));
     OTH_CHECK_CUDA(cudaMallocHost((void**)&h_counters, 8 * sizeof(unsigned long long)));
+    OTH_CHECK_CUDA(cudaEventCreate(&ev_begin));
+    OTH_CHECK_CUDA(cudaEventCreate(&ev_end));
+    // trajectories of one full house of games; grown by run() when a campaign plays more episodes than there are slots
     d.out = nullptr; d.out_cap = 0;
+    OTH_CHECK_CUDA(cudaMalloc((void**)&d.out, S * kMaxPlies * sizeof(oth_sample)));
+    d.out_cap = (int64_t)S * kMaxPlies;
     return OTH_OK;
 }
 
@@ -234,6 +199,60 @@ void SelfPlayHost::release()
     d.out = nullptr;
     if (h_counters) cudaFreeHost(h_counters);
     h_counters = nullptr;
+    if (ev_begin) cudaEventDestroy(ev_begin);
+    if (ev_end) cudaEventDestroy(ev_end);
+    ev_begin = ev_end = nullptr;
+}
+
+// Which schedule plays the campaign.  Both produce the same records (the search is a deterministic function of the
+// root position and the move draw is keyed on (seed, episode, ply)); they differ in how often the network is launched:
+// lock-step needs (1 + sims) launches per ply but lets identical roots share one search -- the winner when hundreds of
+// thousands of games start together; run-until-miss needs one launch per cache MISS of the slowest slot and wins as
+// long as the network launch, not its throughput, is what a step costs.
+int SelfPlayHost::pick_schedule() const
+{
+    const bool noisy = cfg.add_dirichlet_noise && (cfg.flags & OTH_FLAG_ROOT_N_SUM);   // per-game noise enters the search
+    if (noisy) return OTH_SCHEDULE_LOCKSTEP;
+    if (cfg.schedule == OTH_SCHEDULE_LOCKSTEP || cfg.schedule == OTH_SCHEDULE_ASYNC) return (int)cfg.schedule;
+    const bool cached = (cfg.flags & OTH_FLAG_EVAL_CACHE) && !(cfg.flags & OTH_FLAG_EVAL_HASHNET);
+    return (cached && d.slots <= kAsyncAutoMaxSlots) ? OTH_SCHEDULE_ASYNC : OTH_SCHEDULE_LOCKSTEP;
+}
+
+int SelfPlayHost::run_lockstep(NetHost* net, int64_t num_episodes)
+{
+    const int grid_t = (int)((d.slots + 255) / 256), grid_w = (int)((d.slots + 7) / 8);
+    const int64_t max_moves = (num_episodes + d.slots - 1) / d.slots * kMaxPlies + kMaxPlies;
+    for (int64_t mv = 0;; ++mv) {
+        OTH_REQUIRE(mv <= max_moves, OTH_ERR_STATE, "oth_selfplay_run: games did not terminate");
+        // identical root positions share one search -- unless per-game Dirichlet noise really enters the search
+        const bool noisy = cfg.add_dirichlet_noise && (cfg.flags & OTH_FLAG_ROOT_N_SUM);
+        const int share = (!noisy && !(cfg.flags & OTH_FLAG_NO_SEARCH_SHARING)) ? 1 : 0;
+        ++ply_epoch;
+        k_sp_group_elect<<<grid_t, 256, 0, ctx->stream>>>(d, ply_epoch, share);
+        ctx->launches++;
+        if (share) {
+            k_sp_group_follow<<<grid_t, 256, 0, ctx->stream>>>(d);
+            ctx->launches++;
+        }
+        OTH_CHECK_CUDA(cudaGetLastError());
+        int rc = search.begin(d.self_b, d.opp_b, d.search_active, d.slots);
+        if (rc) return rc;
+        const uint64_t step_seed = mix64(run_seed + (uint64_t)mv * 0x9E3779B97F4A7C15ULL);
+        if ((rc = search.run(net, cfg.num_simulations, cfg.add_dirichlet_noise != 0, step_seed))) return rc;
+        last_ticks += (uint64_t)cfg.num_simulations + 1;
+        {
+            TimedLaunch timed(ctx, 2);
+            k_sp_move<<<grid_w, 256, 0, ctx->stream>>>(d, search.t, num_episodes, cfg.temperature_threshold, run_seed, cfg.flags);
+        }
+        ctx->launches++;
+        OTH_CHECK_CUDA(cudaGetLastError());
+        ++moves_played;
+        OTH_CHECK_CUDA(cudaMemcpyAsync(h_counters, d.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        OTH_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        OTH_REQUIRE(h_counters[5] == 0, OTH_ERR_CAPACITY, "oth_selfplay_run: trajectory buffer overflow");
+        if ((int64_t)h_counters[1] >= num_episodes) break;
+    }
+    return OTH_OK;
 }
 
 int SelfPlayHost::run(NetHost* net, int64_t num_episodes, int64_t* n_samples, int64_t* n_evals)
@@ -251,49 +270,31 @@ int SelfPlayHost::run(NetHost* net, int64_t num_episodes, int64_t* n_samples, in
         OTH_CHECK_CUDA(cudaMalloc((void**)&d.out, (size_t)need * sizeof(oth_sample)));
         d.out_cap = need;
     }
+    // every campaign on this handle draws its moves from its own stream (run 0 uses the configured seed itself)
+    run_seed = runs == 0 ? cfg.seed : mix64(cfg.seed ^ (runs * 0xD6E8FEB86659FD93ULL));
+    ++runs;
     search.invalidate_cache();          // a campaign starts cold: the weights usually changed since the last one
     {
         unsigned long long dummy[4];
         int rc0 = search.read_stats(dummy, true);
         if (rc0) return rc0;
     }
-    const int grid_t = (int)((d.slots + 255) / 256), grid_w = (int)((d.slots + 7) / 8);
-    k_sp_reset<<<grid_t, 256, 0, ctx->stream>>>(d, num_episodes);
+    const uint64_t launches0 = ctx->launches;
+    last_ticks = 0;
+    OTH_CHECK_CUDA(cudaEventRecord(ev_begin, ctx->stream));
+    k_sp_reset<<<(int)((d.slots + 255) / 256), 256, 0, ctx->stream>>>(d, num_episodes);
     ctx->launches++;
     OTH_CHECK_CUDA(cudaGetLastError());
-    const int64_t max_moves = (num_episodes + d.slots - 1) / d.slots * kMaxPlies + kMaxPlies;
-    for (int64_t mv = 0;; ++mv) {
-        OTH_REQUIRE(mv <= max_moves, OTH_ERR_STATE, "oth_selfplay_run: games did not terminate");
-        // identical root positions share one search -- unless per-game Dirichlet noise really enters the search
-        const bool noisy = cfg.add_dirichlet_noise && (cfg.flags & OTH_FLAG_ROOT_N_SUM);
-        const int share = (!noisy && !(cfg.flags & OTH_FLAG_NO_SEARCH_SHARING)) ? 1 : 0;
-        ++ply_epoch;
-        k_sp_group_elect<<<grid_t, 256, 0, ctx->stream>>>(d, ply_epoch, share);
-        ctx->launches++;
-        if (share) {
-            k_sp_group_follow<<<grid_t, 256, 0, ctx->stream>>>(d);
-            ctx->launches++;
-        }
-        OTH_CHECK_CUDA(cudaGetLastError());
-        int rc = search.begin(d.self_b, d.opp_b, d.search_active, d.slots);
-        if (rc) return rc;
-        const uint64_t step_seed = mix64(cfg.seed + (uint64_t)mv * 0x9E3779B97F4A7C15ULL);
-        if ((rc = search.run(net, cfg.num_simulations, cfg.add_dirichlet_noise != 0, step_seed))) return rc;
-        {
-            TimedLaunch timed(ctx, 2);
-            k_sp_move<<<grid_w, 256, 0, ctx->stream>>>(d, search.t, num_episodes, cfg.temperature_threshold, cfg.seed, cfg.flags);
-        }
-        ctx->launches++;
-        OTH_CHECK_CUDA(cudaGetLastError());
-        ++moves_played;
-        OTH_CHECK_CUDA(cudaMemcpyAsync(h_counters, d.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-        OTH_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-        OTH_REQUIRE(h_counters[5] == 0, OTH_ERR_CAPACITY, "oth_selfplay_run: trajectory buffer overflow");
-        if ((int64_t)h_counters[1] >= num_episodes) break;
-    }
-    int rc = search.check_overflow();
+    last_schedule = pick_schedule();
+    int rc = last_schedule == OTH_SCHEDULE_ASYNC ? run_async(net, num_episodes) : run_lockstep(net, num_episodes);
     if (rc) return rc;
+    OTH_CHECK_CUDA(cudaEventRecord(ev_end, ctx->stream));
+    if ((rc = search.check_overflow())) return rc;        // synchronises the stream
     if ((rc = search.read_stats(last_stats, false))) return rc;
+    float ms = 0.f;
+    OTH_CHECK_CUDA(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+    last_run_ms = (double)ms;
+    last_launches = ctx->launches - launches0;
     last_searches = (uint64_t)h_counters[6];
     last_samples = (int64_t)h_counters[2];
     if (n_samples) *n_samples = last_samples;
@@ -304,8 +305,6 @@ int SelfPlayHost::run(NetHost* net, int64_t num_episodes, int64_t* n_samples, in
 }  // namespace oth
 
 using namespace oth;
-
-struct oth_selfplay : public oth::SelfPlayHost {};
 
 extern "C" {
 
@@ -337,11 +336,29 @@ int oth_selfplay_run(oth_selfplay* sp, oth_net* net, int64_t num_episodes, int64
     return sp->run(net, num_episodes, n_samples_out, n_evals_out);
 }
 
-int oth_selfplay_stats(oth_selfplay* sp, uint64_t* out4)
+int oth_selfplay_stats(oth_selfplay* sp, uint64_t* out5)
 {
-    OTH_REQUIRE(sp && out4, OTH_ERR_ARG, "oth_selfplay_stats: NULL argument");
-    for (int i = 0; i < 4; ++i) out4[i] = sp->last_stats[i];
-    out4[4] = sp->last_searches;
+    OTH_REQUIRE(sp && out5, OTH_ERR_ARG, "oth_selfplay_stats: NULL argument");
+    for (int i = 0; i < 4; ++i) out5[i] = sp->last_stats[i];
+    out5[4] = sp->last_searches;
+    return OTH_OK;
+}
+
+int oth_selfplay_timing(oth_selfplay* sp, double* out4)
+{
+    OTH_REQUIRE(sp && out4, OTH_ERR_ARG, "oth_selfplay_timing: NULL argument");
+    out4[0] = sp->last_run_ms;
+    out4[1] = (double)sp->last_ticks;
+    out4[2] = (double)sp->last_schedule;
+    out4[3] = (double)sp->last_launches;
+    return OTH_OK;
+}
+
+int oth_selfplay_set_seed(oth_selfplay* sp, uint64_t seed)
+{
+    OTH_REQUIRE(sp, OTH_ERR_ARG, "oth_selfplay_set_seed: NULL handle");
+    sp->cfg.seed = seed;
+    sp->runs = 0;
     return OTH_OK;
 }
 

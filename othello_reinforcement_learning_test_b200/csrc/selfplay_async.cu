@@ -1,0 +1,358 @@
+// selfplay_async.cu -- run-until-miss schedule of the self-play campaign (OTH_SCHEDULE_ASYNC).
+//
+// The lock-step schedule (selfplay.cu) launches the network once per simulation of a ply: 1 + sims launches per ply,
+// whatever the evaluation cache answers.  When few games run (BASELINE config 3: 100 games per iteration) a launch of
+// the 21-layer network costs its LATENCY, not its throughput, and most leaves are cache hits (the previous ply's
+// subtree is searched again after every move, mcts.py:71: no tree reuse).  Here every slot is its own state machine:
+//
+//     root request -> simulations -> move (record, sample / arg-max, play, label + flush at game end, refill) -> next root ...
+//
+// and one launch of k_as_advance drives each slot through as many of those steps as the cache can answer; a slot only
+// stops when its leaf MISSES.  One tick = advance -> assign (elect one evaluator per distinct position) -> network on the
+// compacted misses -> expand (consume + insert).  Ticks per game = misses of that game (~0.3 x expansions) instead of
+// (1 + sims) x plies.  Every search is still the reference's serial search (one simulation of a game in flight, K = 1),
+// so the records equal the lock-step schedule's byte for byte: select/expand/backup restate node.py:62-136 and
+// mcts.py:100-172 exactly as search.cu does, the move step restates parallel_self_play.py:354-405 as k_sp_move does.
+//
+// The table is only READ in k_as_advance and only WRITTEN in k_tree_expand, which are different kernels: no torn entries.
+#include <math.h>
+
+#include "selfplay.cuh"
+
+namespace oth {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int kLanes = 8;                       // lanes per slot (as k_tree_select / k_tree_expand)
+constexpr int kAsBlock = 64;                    // 2 warps = 8 slots per block: small campaigns spread over many SMs
+constexpr int kSlotsPerBlock = kAsBlock / kLanes;
+
+constexpr int kEvalPerGame = 0;                 // evaluator indexed by game (hash-net): no batch slot
+constexpr int kEvalDirect = 1;                  // cache off: a batch slot straight away
+constexpr int kEvalCached = 2;                  // probe the table; misses are resolved by k_tree_assign
+
+struct AsyncParams {
+    int64_t num_episodes;
+    int sims, threshold, max_steps, eval_mode;
+    float c32;
+    uint32_t flags, epoch, gen;
+    uint64_t seed;
+};
+
+// Fresh trees for every slot (mcts.py:71) at the start of a campaign.
+__global__ void __launch_bounds__(256) k_as_begin(SelfPlayDev d, TreeDev t)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g == 0) *t.batch_count = 0;
+    if (g >= t.games) return;
+    const bool live = g < d.slots && d.active[g];
+    t.root_self[g] = live ? d.self_b[g] : 0ULL;
+    t.root_opp[g] = live ? d.opp_b[g] : 0ULL;
+    t.active[g] = live ? 1 : 0;
+    t.n_nodes[g] = 0; t.n_edges[g] = 0; t.n_evals[g] = 0; t.sims_done[g] = 0; t.path_len[g] = 0; t.root_count[g] = 0;
+    t.pending[g] = 0; t.eval_slot[g] = -1;
+}
+
+__device__ __forceinline__ void backup(Edge* E, const int32_t* path, int depth, double v)
+{
+    for (int dd = depth - 1; dd >= 0; --dd) {               // mcts.py:152-168: sign flip per level, root untouched
+        Edge* ed = E + path[dd];
+        ed->n += 1;
+        ed->w += v;
+        v = -v;
+    }
+}
+
+__global__ void __launch_bounds__(kAsBlock) k_as_advance(SelfPlayDev d, TreeDev t, AsyncParams p)
+{
+    const int lane = threadIdx.x & 31, sub = lane & (kLanes - 1);
+    const int64_t g = blockIdx.x * (int64_t)kSlotsPerBlock + (threadIdx.x / kLanes);
+    const int64_t gs = g < d.slots ? g : 0;
+    bool run = g < d.slots && d.active[gs] && !t.pending[gs];
+    Edge* E = t.edges + gs * (int64_t)t.edge_cap;
+    int32_t* path = t.path + gs * t.path_cap;
+
+    for (int step = 0; step < p.max_steps; ++step) {
+        if (!__any_sync(kFull, run)) break;
+        int rc = 0, sd = 0;
+        uint64_t me = 0ULL, you = 0ULL;
+        if (run) { rc = t.root_count[gs]; sd = t.sims_done[gs]; me = t.root_self[gs]; you = t.root_opp[gs]; }
+        const bool do_move = run && rc > 0 && sd >= p.sims;          // the search of this ply is complete
+        const bool do_sim = run && !do_move;                         // root request (rc == 0) or one simulation
+
+        // ---------------- descent (node.py:91-126, mcts.py:117-123), as k_tree_select ----------------
+        int depth = 0;
+        {
+            int first = 0, cnt = (do_sim && rc > 0) ? rc : 0;
+            int parent_n = (p.flags & OTH_FLAG_ROOT_N_SUM) ? sd : 0;   // mcts.py:152-172: the root is never updated
+            bool descending = cnt > 0;
+            while (__any_sync(kFull, descending)) {
+                const double root_of_n = sqrt((double)parent_n);
+                double best = -INFINITY;
+                int best_e = 0x7FFFFFFF, b_n = 0, b_first = kEdgeLeaf, b_cnt = 0, b_act = 0;
+                if (descending) {
+                    for (int k = sub; k < cnt; k += kLanes) {
+                        const Edge ed = E[first + k];
+                        double q = ed.n ? ed.w / (double)ed.n : 0.0;                    // node.py:51-60
+                        if (p.flags & OTH_FLAG_Q_CANONICAL) q = -q;
+                        const float cp = __fmul_rn(p.c32, ed.p);                        // float32 product (weak Python scalar)
+                        const double u = __ddiv_rn(__dmul_rn((double)cp, root_of_n), (double)(1 + ed.n));
+                        const double sc = __dadd_rn(q, u);
+                        if (sc > best) {                                                // strict >: first maximum wins
+                            best = sc; best_e = first + k; b_n = ed.n; b_first = ed.child_first; b_cnt = ed.child_count; b_act = ed.action;
+                        }
+                    }
+                }
+                int win_lane = sub;
+#pragma unroll
+                for (int o = kLanes / 2; o > 0; o >>= 1) {
+                    const double os = __shfl_xor_sync(kFull, best, o, kLanes);
+                    const int oe = __shfl_xor_sync(kFull, best_e, o, kLanes);
+                    const int ol = __shfl_xor_sync(kFull, win_lane, o, kLanes);
+                    if (os > best || (os == best && oe < best_e)) { best = os; best_e = oe; win_lane = ol; }
+                }
+                const int w_n = __shfl_sync(kFull, b_n, win_lane, kLanes);
+                const int w_first = __shfl_sync(kFull, b_first, win_lane, kLanes);
+                const int w_cnt = __shfl_sync(kFull, b_cnt, win_lane, kLanes);
+                const int w_act = __shfl_sync(kFull, b_act, win_lane, kLanes);
+                if (descending) {
+                    parent_n = w_n;
+                    cnt = w_cnt;
+                    if (sub == 0) path[depth] = best_e;
+                    ++depth;
+                    apply_known_legal(me, you, w_act);                                  // mcts.py:122
+                    if (cnt == 0 || depth >= t.path_cap) descending = false;            // child not expanded: this is the leaf
+                    else first = w_first;
+                }
+            }
+        }
+
+        // ---------------- leaf: terminal backup, table hit (expand now), or a request for the network ----------------
+        if (__any_sync(kFull, do_sim)) {
+            uint64_t lg = 0ULL;
+            bool terminal = false;
+            if (do_sim) {
+                lg = legal_moves(me, you);
+                terminal = depth > 0 && lg == 0 && legal_moves(you, me) == 0;           // mcts.py:127 (a root is never terminal here)
+            }
+            __syncwarp();                                                               // path[] of this descent is visible to lane 0
+            if (do_sim && terminal) {
+                if (sub == 0) {
+                    backup(E, path, depth, (double)winner(me, you));                    // mcts.py:129-130: terminal leaves are re-scored, never expanded
+                    t.sims_done[gs] = sd + 1;
+                }
+            } else if (do_sim) {
+                uint32_t h = 0;
+                bool hit = false;
+                if (p.eval_mode == kEvalCached) {
+                    h = cache_index(t, me, you);
+                    const ulonglong2 key = t.c_key[h];
+                    hit = key.x == me && key.y == you && t.c_gen[h] == p.gen;
+                }
+                if (hit) {
+                    const float* prow = t.c_priors + (size_t)h * 68;                    // masked, renormalised priors as the network wrote them
+                    const int cnt = lg ? popc64(lg) : 1;                                // [64] = forced pass (bitboard.pyx:176-178)
+                    const int first = t.n_edges[gs];
+                    if (first + cnt > t.edge_cap) {
+                        if (sub == 0) atomicExch(t.error_flag, 1);
+                        run = false;
+                    } else {
+                        for (int k = sub; k < cnt; k += kLanes) {                       // node.py:62-89
+                            Edge ed;
+                            ed.w = 0.0; ed.n = 0; ed.child_first = kEdgeLeaf; ed.child_count = 0; ed.pad = 0;
+                            const int action = lg ? nth_set_bit(lg, k) : kPass;
+                            ed.p = prow[action]; ed.action = (uint8_t)action;
+                            E[first + k] = ed;
+                        }
+                        if (sub == 0) {
+                            t.n_nodes[gs] += 1;
+                            t.n_edges[gs] = first + cnt;
+                            t.n_evals[gs] += 1;                                         // what the reference would have evaluated
+                            if (depth == 0) {
+                                t.root_count[gs] = cnt;
+                            } else {
+                                Edge* leaf = E + path[depth - 1];
+                                leaf->child_first = first; leaf->child_count = (uint8_t)cnt;
+                                backup(E, path, depth, (double)t.c_value[h]);           // value.item(), mcts.py:144
+                                t.sims_done[gs] = sd + 1;
+                            }
+                            atomicAdd(&t.stats[1], 1ULL);
+                        }
+                    }
+                } else {
+                    if (sub == 0) {
+                        t.leaf_self[gs] = me; t.leaf_opp[gs] = you; t.leaf_legal[gs] = lg;
+                        t.path_len[gs] = depth;
+                        t.pending[gs] = 1;
+                        if (p.eval_mode == kEvalCached) {
+                            t.leaf_h[gs] = h;
+                            t.leaf_src[gs] = kSrcMiss;
+                            atomicMin(&t.c_owner[h], ((unsigned long long)(~p.epoch) << 32) | (unsigned long long)(uint32_t)gs);
+                        } else if (p.eval_mode == kEvalDirect) {
+                            const int slot = atomicAdd(t.batch_count, 1);
+                            t.batch_self[slot] = me; t.batch_opp[slot] = you; t.eval_slot[gs] = slot;
+                            t.leaf_src[gs] = kSrcSlot;
+                            atomicAdd(&t.stats[0], 1ULL);
+                        }
+                    }
+                    run = false;                                                        // until the evaluation arrives
+                }
+            }
+        }
+
+        // ---------------- move (parallel_self_play.py:354-405), as k_sp_move ----------------
+        if (__any_sync(kFull, do_move)) {
+            const int cnt = do_move ? rc : 0;
+            int ply = 0, game = 0;
+            if (do_move) { ply = d.move_count[gs]; game = d.game_id[gs]; }
+            int total = 0, best_n = -1, best_k = 0x7FFFFFFF;
+            for (int k = sub; k < cnt; k += kLanes) {
+                const int nv = E[k].n;
+                total += nv;
+                if (nv > best_n) { best_n = nv; best_k = k; }                           // np.argmax: first maximum (:380)
+            }
+#pragma unroll
+            for (int o = kLanes / 2; o > 0; o >>= 1) {
+                total += __shfl_xor_sync(kFull, total, o, kLanes);
+                const int on = __shfl_xor_sync(kFull, best_n, o, kLanes);
+                const int ok = __shfl_xor_sync(kFull, best_k, o, kLanes);
+                if (on > best_n || (on == best_n && ok < best_k)) { best_n = on; best_k = ok; }
+            }
+            oth_sample* smp = d.staging + gs * kMaxPlies + (ply < kMaxPlies ? ply : kMaxPlies - 1);
+            // ---- record (state, visit distribution, player): :364,385-388
+            if (do_move) for (int j = sub; j < OTH_ACTIONS; j += kLanes) smp->visits[j] = 0;
+            __syncwarp();
+            if (do_move) for (int k = sub; k < cnt; k += kLanes) smp->visits[E[k].action] = (uint16_t)E[k].n;
+            int pick = best_k;
+            if (do_move && sub == 0) {
+                smp->self_b = me; smp->opp_b = you; smp->legal = legal_moves(me, you);
+                smp->game = game; smp->ply = (int16_t)ply; smp->value = 0; smp->n_children = (uint8_t)cnt;
+                smp->pad[0] = smp->pad[1] = smp->pad[2] = 0;
+                atomicAdd(&d.counters[4], (unsigned long long)t.n_evals[gs]);
+                atomicAdd(&d.counters[6], 1ULL);
+                if (ply >= kMaxPlies) atomicExch(&d.counters[5], 1ULL);
+                // ---- choose the move (:379-382)
+                if (ply < p.threshold && total > 0) {
+                    const uint64_t r = move_draw(p.seed, game, ply);
+                    int target = (int)(((r >> 32) * (uint64_t)total) >> 32);            // uniform in [0,total)
+                    pick = cnt - 1;
+                    for (int k = 0; k < cnt; ++k) {
+                        const int nv = E[k].n;
+                        if (target < nv) { pick = k; break; }
+                        target -= nv;
+                    }
+                }
+            }
+            pick = __shfl_sync(kFull, pick, 0, kLanes);
+            bool over = false;
+            int plies = 0;
+            if (do_move) {
+                apply_known_legal(me, you, (int)E[pick].action);                        // game.board.make_move(action) (:391)
+                plies = ply + 1;
+                over = legal_moves(me, you) == 0 && legal_moves(you, me) == 0;          // :395
+                if (!over && sub == 0) { d.self_b[gs] = me; d.opp_b[gs] = you; d.move_count[gs] = plies; }
+            }
+            // ---- game over: label and flush the trajectory (:397-404)
+            int wv = 0, n_rec = 0;
+            oth_sample* rec = d.staging + gs * kMaxPlies;
+            __syncwarp();
+            if (over) {
+                wv = winner(me, you);                                                   // perspective of the side to move at the end
+                if ((p.flags & OTH_FLAG_WINNER_BLACK) && (plies & 1)) wv = -wv;
+                n_rec = plies < kMaxPlies ? plies : kMaxPlies;
+                for (int i = sub; i < n_rec; i += kLanes) rec[i].value = (int8_t)(wv * ((i & 1) ? -1 : 1));
+            }
+            __syncwarp();
+            unsigned long long base = 0;
+            int next_game = -1;
+            if (over && sub == 0) {
+                base = atomicAdd(&d.counters[2], (unsigned long long)n_rec);
+                atomicAdd(&d.counters[3], (unsigned long long)plies);
+                const unsigned long long id = atomicAdd(&d.counters[0], 1ULL);
+                next_game = id < (unsigned long long)p.num_episodes ? (int)id : -1;
+            }
+            base = __shfl_sync(kFull, base, 0, kLanes);
+            next_game = __shfl_sync(kFull, next_game, 0, kLanes);
+            if (over) {
+                if ((int64_t)(base + n_rec) <= d.out_cap) {
+                    const uint2* src = reinterpret_cast<const uint2*>(rec);
+                    uint2* dst = reinterpret_cast<uint2*>(d.out + base);
+                    const int words = n_rec * (int)(sizeof(oth_sample) / 8);
+                    for (int i = sub; i < words; i += kLanes) dst[i] = src[i];
+                } else if (sub == 0) {
+                    atomicExch(&d.counters[5], 1ULL);
+                }
+            }
+            __syncwarp();
+            if (over) {
+                if (sub == 0) {
+                    __threadfence();
+                    atomicAdd(&d.counters[1], 1ULL);
+                    d.self_b[gs] = kStartSelf; d.opp_b[gs] = kStartOpp; d.move_count[gs] = 0;
+                    d.game_id[gs] = next_game;
+                    d.active[gs] = next_game >= 0 ? 1 : 0;
+                }
+                me = kStartSelf; you = kStartOpp;                                       // board_class(); board.reset() (:338-341)
+                if (next_game < 0) run = false;                                         // the campaign has no episode left for this slot
+            }
+            if (do_move && sub == 0) {                                                  // a fresh tree for the next search (mcts.py:71)
+                t.root_self[gs] = me; t.root_opp[gs] = you;
+                t.n_nodes[gs] = 0; t.n_edges[gs] = 0; t.n_evals[gs] = 0; t.sims_done[gs] = 0; t.path_len[gs] = 0;
+                t.root_count[gs] = 0; t.eval_slot[gs] = -1;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+int SelfPlayHost::run_async(NetHost* net, int64_t num_episodes)
+{
+    SearchHost& s = search;
+    const bool hash = (cfg.flags & OTH_FLAG_EVAL_HASHNET) != 0;
+    const bool use_cache = !hash && s.cache_on && (cfg.flags & OTH_FLAG_EVAL_CACHE);
+    s.n = d.slots; s.n_act = d.slots; s.t.act_list = nullptr;
+    s.begun = true; s.awaiting_apply = false; s.root_pending = false;
+    k_as_begin<<<(int)((s.t.games + 255) / 256), 256, 0, ctx->stream>>>(d, s.t);
+    ctx->launches++;
+    OTH_CHECK_CUDA(cudaGetLastError());
+
+    AsyncParams p{};
+    p.num_episodes = num_episodes;
+    p.sims = cfg.num_simulations; p.threshold = cfg.temperature_threshold;
+    p.max_steps = 2 * (cfg.num_simulations + 2);         // at most about two plies' worth of hits per launch: bounds the tail
+    p.eval_mode = hash ? kEvalPerGame : (use_cache ? kEvalCached : kEvalDirect);
+    p.c32 = (float)cfg.c_puct; p.flags = cfg.flags; p.seed = run_seed;
+    TreeDev view = s.t;
+    if (!use_cache) view.cache_mask = 0;
+
+    const int grid = (int)((d.slots + kSlotsPerBlock - 1) / kSlotsPerBlock);
+    const int check_every = 8;                            // termination is polled, not awaited: the launch queue stays full
+    // every tick resolves at least one simulation of every unfinished slot
+    const int64_t rounds = (num_episodes + d.slots - 1) / d.slots + 1;
+    const int64_t max_ticks = rounds * kMaxPlies * (int64_t)(cfg.num_simulations + 3) + 64;
+    for (int64_t tick = 0;; ++tick) {
+        OTH_REQUIRE(tick <= max_ticks, OTH_ERR_STATE, "oth_selfplay_run: games did not terminate");
+        ++s.epoch;
+        p.epoch = s.epoch; p.gen = s.generation;
+        {
+            TimedLaunch timed(ctx, 1);
+            k_as_advance<<<grid, kAsBlock, 0, ctx->stream>>>(d, view, p);
+        }
+        ctx->launches++;
+        OTH_CHECK_CUDA(cudaGetLastError());
+        int rc;
+        if (use_cache && (rc = s.assign())) return rc;
+        if ((rc = s.evaluate(net))) return rc;
+        if ((rc = s.expand(s.t.eval_policy, s.t.eval_value, hash, !hash))) return rc;
+        ++last_ticks;
+        if ((tick + 1) % check_every == 0) {
+            OTH_CHECK_CUDA(cudaMemcpyAsync(h_counters, d.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+            OTH_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+            OTH_REQUIRE(h_counters[5] == 0, OTH_ERR_CAPACITY, "oth_selfplay_run: trajectory buffer overflow");
+            if ((int64_t)h_counters[1] >= num_episodes) break;
+        }
+    }
+    moves_played += (uint64_t)h_counters[6];
+    return OTH_OK;
+}
+
+}  // namespace oth

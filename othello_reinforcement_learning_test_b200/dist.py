@@ -48,14 +48,18 @@ def broadcast_weights(model: torch.nn.Module, src: int = 0) -> int:
 
 def all_gather_samples(samples: np.ndarray) -> np.ndarray:
     """All-gather variable-length packed sample arrays; every rank gets the concatenation in
-    rank order."""
+    rank order with GLOBALLY UNIQUE episode ids: rank r's `game` field is offset by the number of
+    episodes of the ranks below it (every rank numbers its own episodes from 0), so grouping or
+    sorting by (game, ply) downstream never interleaves two ranks' games."""
     assert samples.dtype == SAMPLE_DTYPE
     world = dist.get_world_size()
     dev = _comm_device()
-    count = torch.tensor([samples.size], dtype=torch.int64, device=dev)
+    episodes = int(samples["game"].max()) + 1 if samples.size else 0
+    count = torch.tensor([samples.size, episodes], dtype=torch.int64, device=dev)
     counts = [torch.zeros_like(count) for _ in range(world)]
     dist.all_gather(counts, count)
-    counts = [int(c.item()) for c in counts]
+    episodes_per_rank = [int(c[1].item()) for c in counts]
+    counts = [int(c[0].item()) for c in counts]
     biggest = max(counts) if counts else 0
     rec = SAMPLE_DTYPE.itemsize
     buf = torch.zeros(max(biggest, 1) * rec, dtype=torch.uint8, device=dev)
@@ -63,10 +67,13 @@ def all_gather_samples(samples: np.ndarray) -> np.ndarray:
         buf[: samples.size * rec] = torch.from_numpy(samples.view(np.uint8).reshape(-1).copy()).to(dev)
     gathered = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(gathered, buf)
-    parts = [g[: c * rec].cpu().numpy().view(SAMPLE_DTYPE) for g, c in zip(gathered, counts)]
-    out = np.concatenate(parts) if parts else np.empty(0, SAMPLE_DTYPE)
-    # make episode ids globally unique: offset by the episodes of the lower ranks
-    return out
+    parts, base = [], 0
+    for g, c, e in zip(gathered, counts, episodes_per_rank):
+        part = g[: c * rec].cpu().numpy().view(SAMPLE_DTYPE).copy()
+        part["game"] += base
+        base += e
+        parts.append(part)
+    return np.concatenate(parts) if parts else np.empty(0, SAMPLE_DTYPE)
 
 
 class _DevView:
@@ -76,22 +83,34 @@ class _DevView:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
 
 
-def all_gather_samples_device(dev_ptr: int, count: int, device: torch.device):
+_GAME_WORD = SAMPLE_DTYPE.fields["game"][1] // 4          # int32 index of the `game` field inside a record
+_REC_WORDS = SAMPLE_DTYPE.itemsize // 4
+
+
+def all_gather_samples_device(dev_ptr: int, count: int, device: torch.device, episodes: int | None = None):
     """All-gather packed samples that already live in device memory (oth_selfplay_samples_device) without a host
     hop: returns (uint8 CUDA tensor holding every rank's records back to back in rank order, total count).
-    Feed it to a device ReplayBuffer with `oth_replay_add(..., OTH_MEM_DEVICE)`."""
+    Feed it to a device ReplayBuffer with `ReplayBuffer.add_device`.  `episodes` = how many episodes this rank
+    played: when given, the `game` fields are offset on the device so that episode ids are globally unique."""
     world = dist.get_world_size()
     rec = SAMPLE_DTYPE.itemsize
-    cnt = torch.tensor([count], dtype=torch.int64, device=device)
+    cnt = torch.tensor([count, -1 if episodes is None else episodes], dtype=torch.int64, device=device)
     counts = [torch.zeros_like(cnt) for _ in range(world)]
     dist.all_gather(counts, cnt)
-    counts = [int(c.item()) for c in counts]
+    episodes_per_rank = [int(c[1].item()) for c in counts]
+    counts = [int(c[0].item()) for c in counts]
     biggest = max(max(counts), 1)
     mine = torch.zeros(biggest * rec, dtype=torch.uint8, device=device)
     if count:
         mine[: count * rec] = torch.as_tensor(_DevView(dev_ptr, count * rec), device=device)
     gathered = torch.empty(world * biggest * rec, dtype=torch.uint8, device=device)
     dist.all_gather_into_tensor(gathered, mine)
+    if all(e >= 0 for e in episodes_per_rank):
+        words = gathered.view(torch.int32).view(world, biggest, _REC_WORDS)
+        base = 0
+        for r in range(1, world):
+            base += episodes_per_rank[r - 1]
+            words[r, : counts[r], _GAME_WORD] += base
     if all(c == biggest for c in counts):
         return gathered, sum(counts)
     packed = torch.cat([gathered[r * biggest * rec: r * biggest * rec + c * rec] for r, c in enumerate(counts)])

@@ -199,7 +199,8 @@ class InferenceNet:
             n = s.size
             pol = np.empty((n, 65), np.float32); val = np.empty((n,), np.float32)
             mem = MEM_HOST
-        check(self.ctx.lib.oth_net_forward(self.handle, ptr(s), ptr(o), n, ptr(pol), ptr(val), kind, mem))
+        with _lib.torch_order(self.ctx, s, o, pol, val):      # CUDA tensors: ordered with torch's current stream
+            check(self.ctx.lib.oth_net_forward(self.handle, ptr(s), ptr(o), n, ptr(pol), ptr(val), kind, mem))
         return pol, val
 
     def close(self) -> None:

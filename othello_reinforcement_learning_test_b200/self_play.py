@@ -34,19 +34,27 @@ def planes_from_bits(self_b: np.ndarray, opp_b: np.ndarray, legal: np.ndarray) -
     return bits.reshape(-1, 3, 8, 8).astype(np.float32)
 
 
-def samples_to_training_data(samples: np.ndarray) -> List[Sample]:
-    """Packed oth_sample records -> the reference's list of (state, policy, value), ordered by
-    (episode, ply) like parallel_self_play.py:399-405."""
-    if samples.size == 0:
-        return []
-    order = np.lexsort((samples["ply"], samples["game"]))
-    smp = samples[order]
-    states = planes_from_bits(smp["self_b"], smp["opp_b"], smp["legal"])
-    counts = smp["visits"].astype(np.float32)
+def samples_to_arrays(samples: np.ndarray, sort: bool = True):
+    """Packed oth_sample records -> (states f32[n,3,8,8], policies f32[n,65], values f64[n]) in (episode, ply)
+    order: the three arrays the reference's list of tuples is made of, built with a handful of vectorised numpy
+    calls (no per-sample Python)."""
+    if sort and samples.size:
+        samples = samples[np.lexsort((samples["ply"], samples["game"]))]
+    states = planes_from_bits(samples["self_b"], samples["opp_b"], samples["legal"])
+    counts = samples["visits"].astype(np.float32)
     totals = counts.sum(axis=1, keepdims=True, dtype=np.float32)
     policies = np.divide(counts, totals, out=np.zeros_like(counts), where=totals > 0)   # node.py:177-180
-    values = smp["value"].astype(np.float64)
-    return [(states[i], policies[i], float(values[i])) for i in range(smp.size)]
+    return states, policies, samples["value"].astype(np.float64)
+
+
+def samples_to_training_data(samples: np.ndarray) -> List[Sample]:
+    """Packed oth_sample records -> the reference's list of (state, policy, value), ordered by
+    (episode, ply) like parallel_self_play.py:399-405.  The tuples hold views into three big arrays
+    (`zip` over their rows); the only per-sample Python work is creating the tuple itself."""
+    if samples.size == 0:
+        return []
+    states, policies, values = samples_to_arrays(samples)
+    return list(zip(states, policies, values.tolist()))
 
 
 class SelfPlayEngine:
@@ -54,11 +62,11 @@ class SelfPlayEngine:
 
     def __init__(self, ctx: Context, num_simulations: int, temperature_threshold: int, concurrent_games: int,
                  c_puct: float, dirichlet_alpha: float, dirichlet_epsilon: float, add_dirichlet_noise: bool,
-                 flags: int, seed: int):
+                 flags: int, seed: int, schedule: int = _lib.SCHEDULE_AUTO):
         self.ctx = ctx
         self.cfg = SelfPlayConfig(int(num_simulations), int(temperature_threshold), int(bool(add_dirichlet_noise)),
                                   int(concurrent_games), float(c_puct), float(dirichlet_alpha), float(dirichlet_epsilon),
-                                  int(flags), 0, int(seed) & (2**64 - 1))
+                                  int(flags), int(schedule), int(seed) & (2**64 - 1))
         h = C.c_void_p()
         check(ctx.lib.oth_selfplay_create(ctx.handle, C.byref(self.cfg), C.byref(h)))
         self.handle = h
@@ -73,18 +81,37 @@ class SelfPlayEngine:
             self._pinned = buf = torch.empty(int(need * 1.1) + 4096, dtype=torch.uint8, pin_memory=True)
         return buf.numpy()[:int(n) * _lib.SAMPLE_DTYPE.itemsize].view(_lib.SAMPLE_DTYPE)
 
-    def run(self, net_handle, num_episodes: int, reuse_buffer: bool = False) -> np.ndarray:
-        """reuse_buffer=True returns a view into the engine's pinned buffer, valid until the next run()."""
+    def set_seed(self, seed: int) -> None:
+        """New move-sampling seed for the next campaign (the handle and its buffers stay)."""
+        check(self.ctx.lib.oth_selfplay_set_seed(self.handle, int(seed) & (2**64 - 1)))
+
+    def play(self, net_handle, num_episodes: int) -> int:
+        """One campaign on the device; the records stay there.  Returns the number of samples."""
         ns, ne = C.c_int64(0), C.c_int64(0)
         check(self.ctx.lib.oth_selfplay_run(self.handle, net_handle, int(num_episodes), C.byref(ns), C.byref(ne)))
         self.last_n_evals = int(ne.value)
         st = (C.c_uint64 * 5)()
         check(self.ctx.lib.oth_selfplay_stats(self.handle, st))
+        tm = (C.c_double * 4)()
+        check(self.ctx.lib.oth_selfplay_timing(self.handle, tm))
         self.last_stats = {"nn_positions": int(st[0]), "cache_hits": int(st[1]), "same_step_duplicates": int(st[2]),
-                           "hash_collisions": int(st[3]), "searches_run": int(st[4])}
-        out = self._pinned_out(int(ns.value)) if reuse_buffer else np.empty(int(ns.value), _lib.SAMPLE_DTYPE)
+                           "hash_collisions": int(st[3]), "searches_run": int(st[4]), "device_ms": float(tm[0]),
+                           "network_launches": int(tm[1]), "schedule": {1: "lockstep", 2: "async"}.get(int(tm[2]), "?"),
+                           "kernel_launches": int(tm[3])}
+        self.last_n_samples = int(ns.value)
+        return self.last_n_samples
+
+    def fetch(self, reuse_buffer: bool = False) -> np.ndarray:
+        """Device -> host copy of the last campaign's records (reuse_buffer=True: into the engine's pinned buffer)."""
+        n = self.last_n_samples
+        out = self._pinned_out(n) if reuse_buffer else np.empty(n, _lib.SAMPLE_DTYPE)
         check(self.ctx.lib.oth_selfplay_fetch(self.handle, ptr(out), out.size, MEM_HOST))
         return out
+
+    def run(self, net_handle, num_episodes: int, reuse_buffer: bool = False) -> np.ndarray:
+        """reuse_buffer=True returns a view into the engine's pinned buffer, valid until the next run()."""
+        self.play(net_handle, num_episodes)
+        return self.fetch(reuse_buffer)
 
     def samples_device(self):
         p, n = C.c_void_p(), C.c_int64(0)
@@ -113,7 +140,7 @@ class ParallelSelfPlayWorker:
                  dirichlet_epsilon: float = 0.25, *, concurrent_games: int | None = None, evaluator: str = "auto",
                  winner_black: bool = False, root_n_sum: bool = False, q_canonical: bool = False,
                  engine: str | None = None, seed: int | None = None, verbose: bool = True, eval_cache: bool = True,
-                 share_searches: bool = True, ctx: Context | None = None):
+                 share_searches: bool = True, schedule: str = "auto", ctx: Context | None = None):
         self.board_class = board_class
         self.num_simulations = num_simulations
         self.temperature_threshold = temperature_threshold
@@ -126,6 +153,9 @@ class ParallelSelfPlayWorker:
                                     q_canonical=q_canonical, engine=engine, eval_cache=eval_cache, ctx=ctx)
         self.winner_black = winner_black
         self.share_searches = share_searches      # identical root positions run one search (same results)
+        # "lockstep": 1 + sims network launches per ply; "async": run-until-miss (one launch per cache miss of the
+        # slowest slot); "auto": async up to 32,768 slots when the cache is on.  Same records either way.
+        self.schedule = {"auto": _lib.SCHEDULE_AUTO, "lockstep": _lib.SCHEDULE_LOCKSTEP, "async": _lib.SCHEDULE_ASYNC}[schedule]
         self.seed = seed
         self.verbose = verbose
         self._engine: SelfPlayEngine | None = None
@@ -140,14 +170,17 @@ class ParallelSelfPlayWorker:
         m = self.batch_mcts
         flags = m._flags() | (_lib.FLAG_WINNER_BLACK if self.winner_black else 0) | (
             0 if self.share_searches else _lib.FLAG_NO_SEARCH_SHARING)
-        seed = self.seed if self.seed is not None else int(np.random.randint(0, 2**31 - 1))
+        # The seed is NOT part of the key: trees, staging, the cache and the pinned buffer are kept from campaign to
+        # campaign.  seed=None draws one from numpy when the engine is made (the reference consumes np.random too);
+        # every later campaign on the handle derives its own stream from it, so no two campaigns replay the same draws.
         key = (self._slots_for(num_episodes), self.num_simulations, self.temperature_threshold, m.c_puct,
-               m.dirichlet_alpha, m.dirichlet_epsilon, bool(add_noise), flags, seed)
+               m.dirichlet_alpha, m.dirichlet_epsilon, bool(add_noise), flags, self.schedule)
         if self._engine is None or key != self._engine_key:
             if self._engine is not None:
                 self._engine.close()
+            seed = self.seed if self.seed is not None else int(np.random.randint(0, 2**31 - 1))
             self._engine = SelfPlayEngine(m._context(), self.num_simulations, self.temperature_threshold, key[0],
-                                          m.c_puct, m.dirichlet_alpha, m.dirichlet_epsilon, add_noise, flags, seed)
+                                          m.c_puct, m.dirichlet_alpha, m.dirichlet_epsilon, add_noise, flags, seed, self.schedule)
             self._engine_key = key
         return self._engine
 

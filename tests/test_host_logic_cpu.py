@@ -194,7 +194,9 @@ allv = odist.all_gather_samples(smp)
 assert allv.size == 3 + 5
 assert (allv["ply"][:3] == [0, 1, 2]).all() and (allv["ply"][3:] == [10, 11, 12, 13, 14]).all()
 assert (allv["visits"][:3, 0] == 7).all() and (allv["visits"][3:, 1] == 7).all()
-glob = odist.renumber_games([allv[:3], allv[3:]])
+# episode ids are globally unique after the gather: rank 1's games {0,1} follow rank 0's {0,1}
+assert allv["game"][:3].tolist() == [0, 1, 0] and allv["game"][3:].tolist() == [2, 3, 2, 3, 2]
+glob = odist.renumber_games([smp, smp])
 assert sorted(set(glob["game"].tolist())) == [0, 1, 2, 3]
 dist.barrier()
 dist.destroy_process_group()
