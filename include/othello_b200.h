@@ -117,6 +117,9 @@ int64_t oth_net_param_count(const oth_net* net);
  * eps 1e-5) is folded into bf16 conv weights + fp32 bias inside. */
 int oth_net_load_weights(oth_net* net, const float* flat, int64_t count);
 int oth_net_set_engine(oth_net* net, int engine);
+/* the engine oth_net_forward / the searches will run: OTH_NET_ENGINE_* (tcgen05 for 64 or 128 filters, else the
+ * validation engine), or OTH_ERR_ARG for a NULL handle */
+int oth_net_engine(const oth_net* net);
 /* OthelloResNet.forward on n positions given as bitboards (the (3,8,8) planes are built
  * in-kernel).  policy_out float32 [n,65] in `out_kind`; value_out float32 [n]. */
 int oth_net_forward(oth_net* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n,

@@ -8,11 +8,13 @@ Builds the two CPU checkers:
   into this repo; only the compiled module lands in the git-ignored
   ``oracle/_ref/``).  Skipped when /root/reference is absent (GPU box): the
   prebuilt file travels with the snapshot;
-* ``oracle/_ref/src/**/*.pyc`` -- the REFERENCE'S OWN Python hot-path modules and
+* ``oracle/_ref/src/**/*.rbc`` -- the REFERENCE'S OWN Python hot-path modules and
   their callers (MCTS, network, self-play workers, replay buffer, trainer, arena,
   players), byte-compiled with ``py_compile`` from the sources where they lie
-  (sourceless ``.pyc`` next to the compiled bitboard: outputs only, no reference
-  source text enters the repository or its history).  They let the GPU box run
+  (sourceless byte-code next to the compiled bitboard: outputs only, no reference
+  source text enters the repository or its history; a neutral extension because
+  snapshots to the GPU box drop ``*.pyc`` -- they are copied to ``*.pyc`` in a
+  temp directory when imported).  They let the GPU box run
   the unmodified reference: as the CPU arm of bench.py (``--impl reference``) and
   as the caller side of the drop-in tests (reference arena / self-play / trainer
   code driving this package's classes).
@@ -110,25 +112,45 @@ REF_PY_MODULES = [
 ]
 
 
+REF_BYTECODE_EXT = ".rbc"      # python byte-code under a neutral extension: snapshots to the GPU box drop *.pyc
+
+
+def _materialise_bytecode() -> str | None:
+    """Copy oracle/_ref/**/*.rbc to <tmp>/oth_ref_py/**/*.pyc (importable, sourceless) and return that directory."""
+    if not os.path.exists(os.path.join(REF_OUT, "src", "mcts", "mcts" + REF_BYTECODE_EXT)):
+        return None
+    dst_root = os.path.join(tempfile.gettempdir(), f"oth_ref_py_{os.getuid()}")
+    for rel in REF_PY_MODULES:
+        src = os.path.join(REF_OUT, rel[:-3] + REF_BYTECODE_EXT)
+        dst = os.path.join(dst_root, rel[:-3] + ".pyc")
+        if not os.path.exists(src):
+            return None
+        if not os.path.exists(dst) or os.path.getsize(dst) != os.path.getsize(src) or os.path.getmtime(dst) < os.path.getmtime(src):
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            shutil.copyfile(src, dst + ".tmp")
+            os.replace(dst + ".tmp", dst)
+    return dst_root
+
+
 def ref_python_root() -> str | None:
     """Directory to put on sys.path so that `import src.mcts.mcts` finds the byte-compiled reference."""
-    return REF_OUT if os.path.exists(os.path.join(REF_OUT, "src", "mcts", "mcts.pyc")) else None
+    return _materialise_bytecode()
 
 
 def build_ref_python(force: bool = False) -> str | None:
-    """Byte-compile the reference's Python modules into oracle/_ref (sourceless .pyc, outputs only)."""
+    """Byte-compile the reference's Python modules into oracle/_ref (sourceless byte-code, outputs only)."""
     if not os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "mcts")):
         return ref_python_root()            # GPU box: use what travelled
     import py_compile
     for rel in REF_PY_MODULES:
         src = os.path.join(REFERENCE_ROOT, rel)
-        dst = os.path.join(REF_OUT, rel[:-3] + ".pyc")
+        dst = os.path.join(REF_OUT, rel[:-3] + REF_BYTECODE_EXT)
         if not os.path.exists(src):
             raise RuntimeError(f"reference module {rel} not found under {REFERENCE_ROOT}")
         if not force and os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(src):
             continue
         os.makedirs(os.path.dirname(dst), exist_ok=True)
-        # dfile = the path shown in tracebacks; UNCHECKED_HASH: the .pyc must load without its source
+        # dfile = the path shown in tracebacks; UNCHECKED_HASH: the byte-code must load without its source
         py_compile.compile(src, cfile=dst, dfile=f"<reference>/{rel}", doraise=True,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
     return ref_python_root()

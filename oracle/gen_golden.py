@@ -339,6 +339,72 @@ def gen_net(ref, out, rows):
     print("net_ref written")
 
 
+def bulk_positions(n=10240, seed=123):
+    """`n` distinct self-play positions: games played by the CPU port of the batched worker (C tree, integer test
+    evaluator, 16 simulations, every move sampled), i.e. the kind of position the search hands to the network."""
+    from . import selfplay_port
+    sp = selfplay_port.CpuSelfPlay(None, num_simulations=16, temperature_threshold=200, num_parallel_games=16, seed=seed)
+    pos = set()
+    while len(pos) < n + n // 10:
+        for h in sp.play(16)["samples"]:
+            pos.update((s, o) for (s, o, _, _) in h)
+    pos = sorted(pos)
+    rng = np.random.default_rng(seed)
+    pick = np.sort(rng.choice(len(pos), n, replace=False))
+    S = np.array([pos[i][0] for i in pick], np.uint64); O = np.array([pos[i][1] for i in pick], np.uint64)
+    return S, O
+
+
+def gen_net_bulk(ref, out, n=10240, n_hot=2048):
+    """fp32 outputs of the REFERENCE's own OthelloResNet (10x128) on 10,240 self-play positions: the seed-42
+    initialisation every BASELINE config uses, and -- on the first 2,048 -- the synthetic weights at gain 1.0
+    (saturated policies, p_max ~0.99: the hard case for bf16).  VERDICT r1 item 4(a,b)."""
+    S, O = bulk_positions(n)
+    x = net_oracle.boards_to_tensor(S, O)
+    res = {"self_b": S, "opp_b": O}
+    torch.manual_seed(42)
+    m = ref.OthelloResNet(10, 128); m.eval()
+    with torch.no_grad():
+        lp, v = m(x)
+    lp2, v2 = net_oracle.forward_fp32(m.state_dict(), x)
+    assert torch.equal(lp, lp2) and torch.equal(v, v2)
+    res["init42_10x128_logp"] = lp.numpy(); res["init42_10x128_value"] = v.numpy().reshape(-1)
+    sd = net_oracle.make_state_dict(10, 128, 7, gain=1.0)
+    m = ref.OthelloResNet(10, 128); m.load_state_dict(sd); m.eval()
+    with torch.no_grad():
+        lp, v = m(x[:n_hot])
+    lp2, v2 = net_oracle.forward_fp32(sd, x[:n_hot])
+    assert torch.equal(lp, lp2) and torch.equal(v, v2)
+    res["gain1_10x128_s7_logp"] = lp.numpy(); res["gain1_10x128_s7_value"] = v.numpy().reshape(-1)
+    np.savez_compressed(os.path.join(out, "net_bulk_ref.npz"), **res)
+    print("net_bulk_ref written:", n, "positions; p_max init42", float(np.exp(res["init42_10x128_logp"]).max()),
+          "gain1", float(np.exp(res["gain1_10x128_s7_logp"]).max()))
+
+
+def gen_symmetries(ref, out):
+    """get_symmetries of the compiled reference board (bitboard.pyx:338-370) on 64 positions with random policies:
+    the 8 dihedral images of (planes, pi) in the reference's own order.  Stored as bit-planes + float32 policies."""
+    g = np.load(os.path.join(out, "ref_games.npz"))
+    live = np.flatnonzero(g["terminal"] == 0)
+    idx = np.random.default_rng(8).choice(live, 64, replace=False)
+    S, O = g["self_b"][idx], g["opp_b"][idx]
+    rng = np.random.default_rng(9)
+    pis = rng.random((64, 65)).astype(np.float32)
+    pis /= pis.sum(axis=1, keepdims=True)
+    w = (1 << np.arange(64, dtype=np.uint64))
+    planes = np.zeros((64, 8, 3), np.uint64); pol = np.zeros((64, 8, 65), np.float32)
+    for i in range(64):
+        b = _board(ref, int(S[i]), int(O[i]))
+        sym = b.get_symmetries(pis[i])
+        assert len(sym) == 8
+        for k, (pl, p) in enumerate(sym):
+            assert pl.shape == (3, 8, 8) and p.shape == (65,)
+            planes[i, k] = ((pl.reshape(3, 64) > 0.5).astype(np.uint64) * w).sum(axis=1, dtype=np.uint64)
+            pol[i, k] = p
+    np.savez_compressed(os.path.join(out, "symmetry_ref.npz"), self_b=S, opp_b=O, pi=pis, planes=planes, policy=pol)
+    print("symmetry_ref written")
+
+
 def replay_fixture_data(games):
     """Deterministic training tuples built from the committed reference games (shared with the tests)."""
     rng = np.random.default_rng(99)
@@ -408,6 +474,12 @@ def main():
                 zip(g["game"], g["self_b"], g["opp_b"], g["move_count"], g["legal"], g["action"], g["terminal"], g["winner"])]
         gen_net(ref, OUT, rows)
         return
+    if only == "net_bulk":
+        gen_net_bulk(ref, OUT)
+        return
+    if only == "sym":
+        gen_symmetries(ref, OUT)
+        return
     if only == "replay":
         gen_replay(ref, OUT)
         return
@@ -419,6 +491,8 @@ def main():
     gen_mcts(ref, OUT, rows)
     gen_selfplay(ref, OUT)
     gen_net(ref, OUT, rows)
+    gen_net_bulk(ref, OUT)
+    gen_symmetries(ref, OUT)
     gen_replay(ref, OUT)
     gen_arena(ref, OUT)
     print("golden fixtures written to", OUT)

@@ -80,6 +80,7 @@ _PROTOS = {
     "oth_net_param_count": (_i64, [_p]),
     "oth_net_load_weights": (C.c_int, [_p, _p, _i64]),
     "oth_net_set_engine": (C.c_int, [_p, C.c_int]),
+    "oth_net_engine": (C.c_int, [_p]),
     "oth_net_forward": (C.c_int, [_p, _p, _p, _i64, _p, _p, C.c_int, C.c_int]),
     "oth_search_create": (C.c_int, [_p, _i64, C.c_int, C.POINTER(_p)]),
     "oth_search_destroy": (C.c_int, [_p]),

@@ -353,6 +353,8 @@ int oth_net_load_weights(oth_net* net, const float* flat, int64_t count)
     return net->load(flat, count);
 }
 
+int oth_net_engine(const oth_net* net) { return net ? net->engine : OTH_ERR_ARG; }
+
 int oth_net_set_engine(oth_net* net, int engine)
 {
     OTH_REQUIRE(net, OTH_ERR_ARG, "oth_net_set_engine: net is NULL");

@@ -51,8 +51,11 @@ _OPTIONAL = {
 }
 
 
-def install(force: bool = True, replay_buffer: bool = False, arena: bool = False) -> None:
+def install(force: bool = True, replay_buffer: bool = False, arena: bool = False, only: list | None = None) -> None:
     """Route the hot-path module names of the reference to this package.
+
+    only=[...]: route just these module names (e.g. ["src.cython.bitboard", "src.mcts.mcts", "src.model.net"] keeps the
+    reference's own self-play workers, which then drive this package's board and search).
 
     replay_buffer=True also routes `src.train.buffer` (trainer.py imports ReplayBuffer from there) to the
     device-resident buffer; arena=True routes `src.eval.arena` / `src.eval.players` to the batched arena
@@ -62,7 +65,13 @@ def install(force: bool = True, replay_buffer: bool = False, arena: bool = False
         extra.update(_OPTIONAL["replay_buffer"])
     if arena:
         extra.update(_OPTIONAL["arena"])
-    _install_table({**_REPLACED, **extra}, force)
+    table = {**_REPLACED, **extra}
+    if only is not None:
+        unknown = [n for n in only if n not in table]
+        if unknown:
+            raise ValueError(f"not a routable reference module: {unknown}")
+        table = {n: table[n] for n in only}
+    _install_table(table, force)
 
 
 def _install_table(table, force):

@@ -170,6 +170,12 @@ class InferenceNet:
         code = {"tcgen05": _lib.ENGINE_TCGEN05, "simt": _lib.ENGINE_SIMT, "tcgen05_pair": _lib.ENGINE_TCGEN05_PAIR}[engine]
         check(self.ctx.lib.oth_net_set_engine(self.handle, code))
 
+    @property
+    def engine(self) -> str:
+        """The engine that really runs: "tcgen05" (64 / 128 filters), "tcgen05_pair" or the validation engine "simt"."""
+        code = int(self.ctx.lib.oth_net_engine(self.handle))
+        return {_lib.ENGINE_TCGEN05: "tcgen05", _lib.ENGINE_SIMT: "simt", _lib.ENGINE_TCGEN05_PAIR: "tcgen05_pair"}[code]
+
     def load_state_dict(self, sd) -> None:
         flat = flatten_state_dict(sd)
         check(self.ctx.lib.oth_net_load_weights(self.handle, ptr(flat), flat.size))

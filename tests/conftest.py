@@ -66,6 +66,16 @@ def golden_net():
 
 
 @pytest.fixture(scope="session")
+def golden_net_bulk():
+    return dict(np.load(os.path.join(GOLDEN, "net_bulk_ref.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_symmetry():
+    return dict(np.load(os.path.join(GOLDEN, "symmetry_ref.npz")))
+
+
+@pytest.fixture(scope="session")
 def ctx():
     import othello_reinforcement_learning_test_b200 as pkg
     return pkg.Context.default(0)

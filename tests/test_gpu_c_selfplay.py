@@ -7,16 +7,18 @@ from oracle import cref
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("schedule", ["lockstep", "async"])
 @pytest.mark.parametrize("tag", ["a", "b"])
-def test_deterministic_trace_equals_the_reference(golden_selfplay, tag):
+def test_deterministic_trace_equals_the_reference(golden_selfplay, tag, schedule):
     """temperature_threshold = 0 makes every move an arg-max: the whole game, the stored visit
     distributions and the value labels must equal what the reference's worker produced."""
     import othello_reinforcement_learning_test_b200 as pkg
     g = golden_selfplay
     cp, sims = float(g[f"{tag}_cfg"][0]), int(g[f"{tag}_cfg"][1])
     w = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", num_simulations=sims, temperature_threshold=0,
-                                   num_parallel_games=1, c_puct=cp, seed=1, verbose=False)
+                                   num_parallel_games=1, c_puct=cp, seed=1, verbose=False, schedule=schedule)
     data = w.execute_episodes(3, add_dirichlet_noise=True)        # three identical deterministic games
+    assert w.last_stats["schedule"] == schedule
     n = len(g[f"{tag}_batched_value"])
     assert len(data) == 3 * n
     want_states = cref.tensor_input_batch(g[f"{tag}_batched_self"], g[f"{tag}_batched_opp"])
@@ -41,14 +43,16 @@ def test_serial_worker_equals_the_reference(golden_selfplay):
         assert np.array_equal(pol, g["a_serial_policy"][i]) and val == float(g["a_serial_value"][i])
 
 
-def test_sampled_campaign_is_consistent_under_replay():
+@pytest.mark.parametrize("schedule", ["lockstep", "async"])
+def test_sampled_campaign_is_consistent_under_replay(schedule):
     """With sampling (own RNG, not comparable to numpy's stream) every recorded game must still be a
     legal REF-rules game whose records agree with the oracle ply by ply."""
     import othello_reinforcement_learning_test_b200 as pkg
     sims = 20
     w = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", num_simulations=sims, temperature_threshold=15,
-                                   num_parallel_games=16, c_puct=1.0, seed=5, concurrent_games=64, verbose=False)
+                                   num_parallel_games=16, c_puct=1.0, seed=5, concurrent_games=64, verbose=False, schedule=schedule)
     smp = w.execute_episodes_packed(200, add_dirichlet_noise=True)     # 64 slots, 200 episodes: exercises refill
+    assert w.last_stats["schedule"] == schedule
     assert sorted(set(smp["game"].tolist())) == list(range(200))
     order = np.lexsort((smp["ply"], smp["game"]))
     smp = smp[order]
@@ -114,3 +118,30 @@ def test_winner_black_flag_only_changes_labels():
     plies = a.size
     # REF label: winner is seen from the side to move at the end; black-relative flips it on odd game lengths
     assert np.array_equal(b["value"], a["value"] * (-1 if plies % 2 else 1))
+
+
+def test_async_schedule_produces_the_lockstep_records_hashnet():
+    """Run-until-miss vs lock-step with the integer evaluator: same episodes, same records, byte for byte
+    (refills, sampling before the threshold, c_puct 1.5, 100 simulations: BASELINE config 4's search settings)."""
+    import othello_reinforcement_learning_test_b200 as pkg
+    kw = dict(num_simulations=100, temperature_threshold=20, num_parallel_games=16, c_puct=1.5, seed=9, concurrent_games=40, verbose=False)
+    order = lambda a: a[np.lexsort((a["ply"], a["game"]))]
+    a = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", schedule="lockstep", **kw)
+    b = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", schedule="async", **kw)
+    for n in (100, 7):                                                  # second campaign: derived seed, partly filled slots
+        sa, sb = order(a.execute_episodes_packed(n)), order(b.execute_episodes_packed(n))
+        assert sa.size == sb.size and sa.tobytes() == sb.tobytes()
+        assert a.last_stats["nn_evals"] == b.last_stats["nn_evals"]
+        assert (a.last_stats["schedule"], b.last_stats["schedule"]) == ("lockstep", "async")
+
+
+def test_campaigns_on_one_worker_draw_from_different_streams():
+    """game ids restart at 0 every run, so the run index must enter the sampling hash."""
+    import othello_reinforcement_learning_test_b200 as pkg
+    kw = dict(num_simulations=10, temperature_threshold=15, num_parallel_games=16, seed=5, concurrent_games=32, verbose=False)
+    w = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", **kw)
+    order = lambda a: a[np.lexsort((a["ply"], a["game"]))]
+    first, second = order(w.execute_episodes_packed(32)).copy(), order(w.execute_episodes_packed(32)).copy()
+    assert first.tobytes() != second.tobytes()
+    again = order(pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", **kw).execute_episodes_packed(32))
+    assert again.tobytes() == first.tobytes()                          # same seed, same first campaign

@@ -14,8 +14,8 @@ def _positions(golden_games, n, seed):
     return golden_games["self_b"][idx], golden_games["opp_b"][idx]
 
 
-@pytest.mark.parametrize("nb,nf", [(2, 32), (5, 64)])
-def test_native_search_equals_reference_search_under_identical_network_outputs(ctx, golden_games, nb, nf):
+@pytest.mark.parametrize("nb,nf,engine,n_pos", [(2, 32, "simt", 48), (5, 64, "tcgen05", 48), (10, 128, "tcgen05", 32)])
+def test_native_search_equals_reference_search_under_identical_network_outputs(ctx, golden_games, nb, nf, engine, n_pos):
     """Visit counts of the all-on-device search == visit counts of the reference algorithm (oracle)
     when the oracle is given exactly the network outputs the device network produces."""
     import othello_reinforcement_learning_test_b200 as pkg
@@ -24,14 +24,15 @@ def test_native_search_equals_reference_search_under_identical_network_outputs(c
     model = OthelloResNet(nb, nf).eval()
     m = pkg.MCTS(model, "cuda", c_puct=1.0)
     assert m.evaluator == "native"
-    S, O = _positions(golden_games, 48, 3)
+    S, O = _positions(golden_games, n_pos, 3)
     vis, q, nev = m.search_arrays(S, O, 50)
     net = m._native_net()
+    assert net.engine == engine          # 32 filters: the CUDA-core validation engine; 64 / 128: the tcgen05 product engine
 
     def ev(a, b):
         p, v = net.forward(np.array([a], np.uint64), np.array([b], np.uint64), out="probs")
         return p[0], float(v[0])
-    for i in range(48):
+    for i in range(n_pos):
         res = cref.mcts_search(int(S[i]), int(O[i]), 50, 1.0, evaluator=ev)
         assert np.array_equal(vis[i], res["visits"]), i
         assert nev[i] == res["n_evals"]
@@ -103,6 +104,35 @@ def test_eval_cache_and_dedup_are_result_transparent(ctx, golden_games):
     st = m1._tree.stats()
     assert st["nn_positions"] + st["cache_hits"] + st["same_step_duplicates"] == int(e1.sum())
     assert st["cache_hits"] + st["same_step_duplicates"] > 0
+
+
+@pytest.mark.parametrize("nb,nf,games,slots", [(5, 64, 150, 96), (10, 128, 100, 100)])
+def test_async_schedule_equals_lockstep_with_the_network(ctx, nb, nf, games, slots):
+    """Run-until-miss (cache hits answered inside the advance kernel, one-tile network launches for small batches) must
+    reproduce the lock-step campaign byte for byte -- with the cache on, and against the engine with everything off."""
+    import othello_reinforcement_learning_test_b200 as pkg
+    from othello_reinforcement_learning_test_b200.net import OthelloResNet
+    torch.manual_seed(42)
+    model = OthelloResNet(nb, nf).eval()
+    kw = dict(num_simulations=50, temperature_threshold=15, num_parallel_games=16, seed=33, concurrent_games=slots, verbose=False)
+    order = lambda a: a[np.lexsort((a["ply"], a["game"]))]
+    plain = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, "cuda", eval_cache=False, share_searches=False, schedule="lockstep", **kw)
+    lock = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, "cuda", eval_cache=True, schedule="lockstep", **kw)
+    asyn = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, "cuda", eval_cache=True, schedule="async", **kw)
+    asyn_nc = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, "cuda", eval_cache=False, schedule="async", **kw)
+    want = order(plain.execute_episodes_packed(games))
+    for w in (lock, asyn, asyn_nc):
+        got = order(w.execute_episodes_packed(games))
+        assert got.size == want.size and got.tobytes() == want.tobytes()
+        assert w.last_stats["nn_evals"] == plain.last_stats["nn_evals"]
+    assert asyn.last_stats["schedule"] == "async" and lock.last_stats["schedule"] == "lockstep"
+    # fewer network launches than 1 + sims per ply, and no more network positions than expansions
+    assert asyn.last_stats["network_launches"] < lock.last_stats["network_launches"]
+    assert asyn.last_stats["nn_positions"] + asyn.last_stats["cache_hits"] + asyn.last_stats["same_step_duplicates"] == plain.last_stats["nn_evals"]
+    assert asyn_nc.last_stats["nn_positions"] == plain.last_stats["nn_evals"]
+    auto = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, "cuda", **kw)       # default: cache on, auto schedule
+    got = order(auto.execute_episodes_packed(games))
+    assert got.tobytes() == want.tobytes() and auto.last_stats["schedule"] == "async"
 
 
 def test_packed_campaign_into_the_reusable_pinned_buffer(ctx):

@@ -75,11 +75,16 @@ def test_baseline_sized_campaign_properties(ctx):
     st = w.last_stats
     assert 55 * G < smp.size < 70 * G
     assert 2700 < st["nn_evals"] / G < 3100                                 # the reference measured 2,882 per game
-    assert st["nn_positions"] < 0.5 * st["nn_evals"] and st["searches_run"] < smp.size
+    # 4,736 slots: the auto schedule is run-until-miss (every slot runs its own search, the cache removes the repeats)
+    assert st["schedule"] == "async" and st["searches_run"] == smp.size
+    assert st["nn_positions"] < 0.5 * st["nn_evals"]
+    assert st["network_launches"] < 0.6 * 51 * 61                           # lock-step would need (1 + sims) launches per ply
     _check_campaign(smp, 50, 15, G)
     # the same campaign with every sharing switch off: identical bytes (checked on a smaller slice to keep it short)
     kw = dict(num_simulations=50, temperature_threshold=15, num_parallel_games=16, concurrent_games=384, seed=78, verbose=False)
-    a = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, "cuda", **kw).execute_episodes_packed(384)
+    wa = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, "cuda", schedule="lockstep", **kw)
+    a = wa.execute_episodes_packed(384)
+    assert wa.last_stats["schedule"] == "lockstep" and wa.last_stats["searches_run"] < a.size     # identical roots share a search
     b = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, "cuda", eval_cache=False, share_searches=False,
                                    **kw).execute_episodes_packed(384)
     a = _check_campaign(a, 50, 15, 384)
@@ -120,3 +125,32 @@ def test_symmetry_augmentation_matches_board_symmetries(ctx):
         for k in range(8):
             assert np.array_equal(full[8 * i + k][0], sym[k][0]) and np.array_equal(full[8 * i + k][1], sym[k][1])
             assert full[8 * i + k][2] == val
+
+
+def _planes_to_bits(planes):
+    w8 = (1 << np.arange(64, dtype=np.uint64))
+    return ((np.asarray(planes).reshape(-1, 3, 64) > 0.5).astype(np.uint64) * w8).sum(axis=2, dtype=np.uint64)
+
+
+def test_get_symmetries_equals_the_compiled_reference(ctx, golden_symmetry):
+    """R-BB8: OthelloBitboard.get_symmetries (bitboard.pyx:338-370) -- the 8 dihedral images in the reference's own order,
+    compared with what the compiled reference board returned for 64 positions and random policies
+    (tests/golden/symmetry_ref.npz, oracle/gen_golden.py gen_symmetries); and the full augmentation built from it."""
+    import othello_reinforcement_learning_test_b200 as pkg
+    g = golden_symmetry
+    data = []
+    for i in range(64):
+        b = pkg.OthelloBitboard(); b.self_board = int(g["self_b"][i]); b.opp_board = int(g["opp_b"][i])
+        sym = b.get_symmetries(g["pi"][i])
+        assert len(sym) == 8
+        for k, (pl, p) in enumerate(sym):
+            assert pl.shape == (3, 8, 8) and pl.dtype == np.float32 and p.shape == (65,)
+            assert np.array_equal(_planes_to_bits(pl)[0], g["planes"][i, k]), (i, k)
+            assert np.array_equal(p.astype(np.float32), g["policy"][i, k]), (i, k)
+        data.append((b.get_tensor_input(), g["pi"][i], 1.0 if i % 2 else -1.0))
+    full = pkg.augment_data_with_symmetries(data, pkg.OthelloBitboard, full=True)
+    assert len(full) == 8 * 64
+    for i in range(64):
+        for k in range(8):
+            st, p, v = full[8 * i + k]
+            assert np.array_equal(_planes_to_bits(st)[0], g["planes"][i, k]) and np.array_equal(p, g["policy"][i, k]) and v == data[i][2]
