@@ -258,7 +258,7 @@ def run_leg(pkg, ctx, name, *, blocks=10, filters=128, sims=50, c_puct=1.0, thr=
     ctx.timing_enable(True)
     tot = {"ms": 0.0, "games": 0, "samples": 0, "evals": 0, "pos": 0, "hits": 0, "dups": 0, "searches": 0, "ticks": 0, "launches": 0}
     n = 0
-    while n < max_campaigns and tot["ms"] < 1000.0 * min_seconds:
+    while n < max_campaigns and (n == 0 or tot["ms"] < 1000.0 * min_seconds):
         ns = eng.play(net.handle, games)
         st = eng.last_stats
         tot["ms"] += st["device_ms"]; tot["games"] += games; tot["samples"] += ns; tot["evals"] += eng.last_n_evals

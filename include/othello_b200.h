@@ -83,6 +83,24 @@ int oth_terminal_winner(oth_ctx* ctx, const uint64_t* self_b, const uint64_t* op
 /* get_tensor_input (bitboard.pyx:300-323): float32 [n,3,8,8] = self, opp, legal planes */
 int oth_tensor_input(oth_ctx* ctx, const uint64_t* self_b, const uint64_t* opp_b, float* out,
                      int64_t n, int mem);
+/* ---- the single-board path: one launch per call, no allocation, no copies ---------------------------------
+ * What src/eval/arena.py:106-119 needs per move from OthelloBitboard: make_move(action) (bitboard.pyx:195-247, every
+ * reject path), then get_legal_moves / is_terminal / get_winner / get_stone_counts of the position reached
+ * (:166-193, :249-298).  One one-warp kernel does all of it; arguments travel as kernel parameters, the result lands in a
+ * page-locked mailbox mapped into the device (no cudaMalloc, no memcpy), the host waits on the mailbox's sequence word.
+ * action == OTH_ACTION_NONE: no move, just the state of (self_b, opp_b). */
+#define OTH_ACTION_NONE (-1000)
+typedef struct {
+    uint64_t self_b, opp_b;      /* position after the move (unchanged when it was rejected) */
+    uint64_t legal;              /* get_legal_moves_bits of that position */
+    int32_t move_count;
+    int32_t ok;                  /* make_move's return value (1 for OTH_ACTION_NONE) */
+    int32_t terminal, winner;    /* is_terminal, get_winner (side to move's view) */
+    int32_t self_count, opp_count; /* get_stone_counts */
+    uint64_t seq;                /* mailbox sequence word (internal) */
+} oth_board_state;
+int oth_board_step(oth_ctx* ctx, uint64_t self_b, uint64_t opp_b, int32_t move_count, int32_t action, oth_board_state* out);
+
 /* perft under REF rules (pass = one ply, terminal = leaf); golden values in SURVEY.md 8(c) */
 int oth_perft(oth_ctx* ctx, uint64_t self_b, uint64_t opp_b, int depth, uint64_t* nodes_out);
 /* benchmark.py:18-40 play_random_game x n_games, one game per thread, from the start position.
@@ -235,6 +253,15 @@ int oth_replay_add(oth_replay* r, const oth_sample* samples, int64_t n, int mem)
 /* sample (buffer.py:58-84) for caller-drawn logical indices (0 = oldest): states f32 [n,3,8,8], policies f32 [n,65],
  * values f32 [n] (= [n,1]); idx and outputs live where `mem` says */
 int oth_replay_gather(oth_replay* r, const int64_t* idx, int64_t n, float* states, float* policies, float* values, int mem);
+/* same with symmetry augmentation on the packed records: sym[i] in 0..7 selects the dihedral image 2*k + flip of sample i in
+ * the order of OthelloBitboard.get_symmetries (src/cython/bitboard.pyx:338-370: np.rot90 k times, then np.flip of the
+ * columns); the three bit-planes and the 64 square counts are permuted, the pass count is carried.  This is the
+ * augmentation the reference declares (src/train/self_play.py:166-212) but never wired in. */
+int oth_replay_gather_sym(oth_replay* r, const int64_t* idx, const uint8_t* sym, int64_t n, float* states, float* policies,
+                          float* values, int mem);
+/* OTH_MEM_DEVICE gathers cannot validate their indices on the host: an index outside [0, size) reads entry 0 instead of a
+ * stale ring slot and raises a flag; this call synchronises and returns OTH_ERR_ARG once if the flag is up */
+int oth_replay_check(oth_replay* r);
 int oth_replay_value_stats(oth_replay* r, double* mean_out, double* std_out);  /* get_statistics, buffer.py:102-123 */
 
 /* ---- diagnostics ---------------------------------------------------------------------- */

@@ -38,6 +38,15 @@ class SelfPlayConfig(C.Structure):
     ]
 
 
+class BoardState(C.Structure):
+    """oth_board_state (include/othello_b200.h)"""
+    _fields_ = [("self_b", C.c_uint64), ("opp_b", C.c_uint64), ("legal", C.c_uint64), ("move_count", C.c_int32),
+                ("ok", C.c_int32), ("terminal", C.c_int32), ("winner", C.c_int32), ("self_count", C.c_int32),
+                ("opp_count", C.c_int32), ("seq", C.c_uint64)]
+
+
+ACTION_NONE = -1000
+
 SAMPLE_DTYPE = np.dtype([
     ("self_b", np.uint64), ("opp_b", np.uint64), ("legal", np.uint64),
     ("game", np.int32), ("ply", np.int16), ("value", np.int8), ("n_children", np.uint8),
@@ -64,6 +73,7 @@ _PROTOS = {
     "oth_make_move": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, C.c_int]),
     "oth_terminal_winner": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, C.c_int]),
     "oth_tensor_input": (C.c_int, [_p, _p, _p, _p, _i64, C.c_int]),
+    "oth_board_step": (C.c_int, [_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(BoardState)]),
     "oth_perft": (C.c_int, [_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
     "oth_random_playouts": (C.c_int, [_p, _i64, C.c_uint64, C.POINTER(_i64), C.POINTER(_i64), _p, _p, _p, C.c_int]),
     "oth_choose_random": (C.c_int, [_p, _p, _p, _p, C.c_uint64, _p, _i64, C.c_int]),
@@ -74,6 +84,8 @@ _PROTOS = {
     "oth_replay_clear": (C.c_int, [_p]),
     "oth_replay_add": (C.c_int, [_p, _p, _i64, C.c_int]),
     "oth_replay_gather": (C.c_int, [_p, _p, _i64, _p, _p, _p, C.c_int]),
+    "oth_replay_gather_sym": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, C.c_int]),
+    "oth_replay_check": (C.c_int, [_p]),
     "oth_replay_value_stats": (C.c_int, [_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "oth_net_create": (C.c_int, [_p, C.c_int, C.c_int, C.POINTER(_p)]),
     "oth_net_destroy": (C.c_int, [_p]),

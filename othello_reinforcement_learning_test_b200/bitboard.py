@@ -184,9 +184,15 @@ class BoardBatch:
 # ---------------------------------------------------------------------------------------------
 
 class OthelloBitboard:
-    """Drop-in for `src.cython.bitboard.OthelloBitboard` (bitboard.pxd:11-48)."""
+    """Drop-in for `src.cython.bitboard.OthelloBitboard` (bitboard.pxd:11-48).
 
-    __slots__ = ("_s", "_o", "move_count", "passed", "_legal", "_ctx")
+    Every rule evaluation is one call of `oth_board_step` (one launch, result in a mapped page-locked mailbox: no
+    allocation, no copies): `make_move` applies the move AND returns the legal mask, terminal flag, winner and disc
+    counts of the position reached, so the calls that follow a move in the reference's loops (arena.py:106-119,
+    self_play.py:71-120: is_terminal, get_legal_moves, get_winner, get_stone_counts, get_tensor_input) are answered from
+    that result without touching the GPU again.  Writing `self_board` / `opp_board` drops the cached answers."""
+
+    __slots__ = ("_s", "_o", "move_count", "passed", "_st", "_ctx")
 
     def __init__(self):
         self._ctx = None
@@ -200,7 +206,7 @@ class OthelloBitboard:
     @self_board.setter
     def self_board(self, v: int) -> None:
         self._s = int(v) & 0xFFFFFFFFFFFFFFFF
-        self._legal = None
+        self._st = None
 
     @property
     def opp_board(self) -> int:
@@ -209,7 +215,7 @@ class OthelloBitboard:
     @opp_board.setter
     def opp_board(self, v: int) -> None:
         self._o = int(v) & 0xFFFFFFFFFFFFFFFF
-        self._legal = None
+        self._st = None
 
     def _context(self) -> Context:
         if self._ctx is None:
@@ -222,22 +228,37 @@ class OthelloBitboard:
         self._o = START_OPP
         self.move_count = 0
         self.passed = False
-        self._legal = None
+        self._st = None
 
     # -- rules: all evaluated by the CUDA library ------------------------------------------------
+    def _step(self, action: int) -> "_lib.BoardState":
+        ctx = self._context()
+        st = _lib.BoardState()
+        check(ctx.lib.oth_board_step(ctx.handle, self._s, self._o, int(self.move_count), action, C.byref(st)))
+        return st
+
+    def _state(self) -> "_lib.BoardState":
+        """(legal, terminal, winner, counts) of the current position: cached from the last make_move, else one launch."""
+        st = self._st
+        if st is None:
+            st = self._st = self._step(_lib.ACTION_NONE)
+        return st
+
     def get_legal_moves_bits(self) -> int:
         """bitboard.pyx:187-193"""
-        if self._legal is None:
-            out = legal_moves(np.array([self._s], np.uint64), np.array([self._o], np.uint64), self._context())
-            self._legal = int(out[0])
-        return self._legal
+        return int(self._state().legal)
 
     def get_legal_moves(self) -> list:
         """bitboard.pyx:166-185: ascending squares, or [64] when the side to move must pass."""
-        m = self.get_legal_moves_bits()
+        m = int(self._state().legal)
         if m == 0:
             return [PASS]
-        return [i for i in range(64) if (m >> i) & 1]
+        out = []
+        while m:
+            low = m & -m
+            out.append(low.bit_length() - 1)
+            m ^= low
+        return out
 
     def make_move(self, pos: int) -> bool:
         """bitboard.pyx:195-247: True if applied; False (state untouched) otherwise."""
@@ -245,42 +266,40 @@ class OthelloBitboard:
             pos = int(pos)
         except (TypeError, ValueError):
             return False
-        if pos < -2**31 or pos >= 2**31:
+        if pos < -2**31 or pos >= 2**31 or pos == _lib.ACTION_NONE:
             return False
-        s = np.array([self._s], np.uint64); o = np.array([self._o], np.uint64)
-        mc = np.array([self.move_count], np.int32)
-        ok = make_move(s, o, mc, np.array([pos], np.int32), self._context())
-        if not ok[0]:
+        st = self._step(pos)
+        if not st.ok:
             return False
-        self._s, self._o, self.move_count = int(s[0]), int(o[0]), int(mc[0])
+        self._s, self._o, self.move_count = int(st.self_b), int(st.opp_b), int(st.move_count)
         self.passed = pos == PASS
-        self._legal = None
+        self._st = st                    # the position reached comes with its legal mask / terminal / winner / counts
         return True
 
     def is_terminal(self) -> bool:
         """bitboard.pyx:249-264"""
-        t, _, _ = terminal_winner(np.array([self._s], np.uint64), np.array([self._o], np.uint64), self._context())
-        return bool(t[0])
+        return bool(self._state().terminal)
 
     def get_winner(self) -> int:
         """bitboard.pyx:266-282: +1 side to move has more discs, -1 fewer, 0 equal."""
-        _, w, _ = terminal_winner(np.array([self._s], np.uint64), np.array([self._o], np.uint64), self._context())
-        return int(w[0])
+        return int(self._state().winner)
 
     def get_stone_counts(self) -> tuple:
         """bitboard.pyx:292-298"""
-        _, _, c = terminal_winner(np.array([self._s], np.uint64), np.array([self._o], np.uint64), self._context())
-        return (int(c[0, 0]), int(c[0, 1]))
+        st = self._state()
+        return (int(st.self_count), int(st.opp_count))
 
     def get_tensor_input(self) -> np.ndarray:
-        """bitboard.pyx:300-323: fresh float32 (3,8,8): self, opp, legal."""
-        return tensor_input(np.array([self._s], np.uint64), np.array([self._o], np.uint64), self._context())[0]
+        """bitboard.pyx:300-323: fresh float32 (3,8,8): self, opp, legal.  Pure format expansion of the three words
+        (the legal mask is the kernel's)."""
+        words = np.array([self._s, self._o, int(self._state().legal)], dtype="<u8")
+        return np.unpackbits(words.view(np.uint8).reshape(3, 8), axis=1, bitorder="little").reshape(3, 8, 8).astype(np.float32)
 
     def copy(self) -> "OthelloBitboard":
         """bitboard.pyx:325-336"""
         b = OthelloBitboard.__new__(OthelloBitboard)
         b._ctx = self._ctx
-        b._s, b._o, b.move_count, b.passed, b._legal = self._s, self._o, self.move_count, self.passed, self._legal
+        b._s, b._o, b.move_count, b.passed, b._st = self._s, self._o, self.move_count, self.passed, self._st
         return b
 
     def get_symmetries(self, pi) -> list:

@@ -99,25 +99,48 @@ class ReplayBuffer:
             raise ValueError(f"Buffer size ({n}) is smaller than batch size ({batch_size})")    # buffer.py:71-74
         return np.asarray(random.sample(range(n), batch_size), np.int64)                        # buffer.py:78
 
-    def sample(self, batch_size: int):
-        """buffer.py:58-84 -> numpy (states [B,3,8,8], policies [B,65], values [B,1])"""
+    def sample(self, batch_size: int, augment: bool = False):
+        """buffer.py:58-84 -> numpy (states [B,3,8,8], policies [B,65], values [B,1]).
+        augment=True: every sample comes back as a random one of its 8 dihedral images (see `gather`)."""
         idx = self._draw(batch_size)
-        st = np.empty((batch_size, 3, 8, 8), np.float32); po = np.empty((batch_size, 65), np.float32)
-        va = np.empty((batch_size, 1), np.float32)
-        check(self.ctx.lib.oth_replay_gather(self.handle, ptr(idx), batch_size, ptr(st), ptr(po), ptr(va), MEM_HOST))
+        sym = np.asarray([random.randrange(8) for _ in range(batch_size)], np.uint8) if augment else None
+        return self.gather(idx, sym)
+
+    def gather(self, idx, sym=None):
+        """Expand the samples at logical indices `idx` (0 = oldest); `sym[i]` in 0..7 (optional) selects the dihedral image
+        2*k + flip of sample i in the order of OthelloBitboard.get_symmetries (bitboard.pyx:338-370).  The images are bit
+        permutations applied to the packed 168-byte records inside the gather kernel (csrc/replay.cu): this is the
+        augmentation self_play.py:166-212 declares and never wires in."""
+        idx = np.ascontiguousarray(idx, np.int64)
+        n = int(idx.size)
+        st = np.empty((n, 3, 8, 8), np.float32); po = np.empty((n, 65), np.float32); va = np.empty((n, 1), np.float32)
+        if sym is None:
+            check(self.ctx.lib.oth_replay_gather(self.handle, ptr(idx), n, ptr(st), ptr(po), ptr(va), MEM_HOST))
+        else:
+            sym = np.ascontiguousarray(sym, np.uint8)
+            assert sym.size == n
+            check(self.ctx.lib.oth_replay_gather_sym(self.handle, ptr(idx), ptr(sym), n, ptr(st), ptr(po), ptr(va), MEM_HOST))
         return st, po, va
 
-    def sample_torch(self, batch_size: int, device=None):
+    def sample_torch(self, batch_size: int, device=None, augment: bool = False):
         """Same minibatch as CUDA tensors, written by the gather kernel (for trainer.py:264-269)."""
         import torch
         dev = torch.device(device) if device is not None else torch.device("cuda", self.ctx.device)
         idx = torch.from_numpy(self._draw(batch_size)).to(dev)
+        sym = torch.randint(0, 8, (batch_size,), dtype=torch.uint8, device=dev) if augment else None
         st = torch.empty((batch_size, 3, 8, 8), dtype=torch.float32, device=dev)
         po = torch.empty((batch_size, 65), dtype=torch.float32, device=dev)
         va = torch.empty((batch_size, 1), dtype=torch.float32, device=dev)
-        with _lib.torch_order(self.ctx, idx, st, po, va):     # ordered with torch's stream on the device, no host sync
-            check(self.ctx.lib.oth_replay_gather(self.handle, ptr(idx), batch_size, ptr(st), ptr(po), ptr(va), MEM_DEVICE))
+        with _lib.torch_order(self.ctx, idx, sym, st, po, va):     # ordered with torch's stream on the device, no host sync
+            if sym is None:
+                check(self.ctx.lib.oth_replay_gather(self.handle, ptr(idx), batch_size, ptr(st), ptr(po), ptr(va), MEM_DEVICE))
+            else:
+                check(self.ctx.lib.oth_replay_gather_sym(self.handle, ptr(idx), ptr(sym), batch_size, ptr(st), ptr(po), ptr(va), MEM_DEVICE))
         return st, po, va
+
+    def check(self) -> None:
+        """Raise if a device-side gather (`sample_torch`, device indices) used an index outside [0, len)."""
+        check(self.ctx.lib.oth_replay_check(self.handle))
 
     # ---- bookkeeping --------------------------------------------------------------------------------
     def __len__(self) -> int:

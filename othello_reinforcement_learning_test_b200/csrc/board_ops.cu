@@ -55,6 +55,23 @@ __global__ void __launch_bounds__(kBlock) k_terminal_winner(const uint64_t* __re
     }
 }
 
+// The single-board path: make_move (optional) + everything the callers ask about the position reached, one thread.
+// Arguments are kernel parameters; the result goes to a mapped page-locked mailbox, sequence word last.
+__global__ void k_board_step(uint64_t me, uint64_t you, int move_count, int action, uint64_t seq, oth_board_state* __restrict__ box)
+{
+    if (threadIdx.x != 0) return;
+    int ok = 1;
+    if (action != OTH_ACTION_NONE) ok = make_move(me, you, move_count, action) ? 1 : 0;     // bitboard.pyx:195-247
+    const uint64_t lg = legal_moves(me, you);                                               // :135-158
+    box->self_b = me; box->opp_b = you; box->legal = lg;
+    box->move_count = move_count; box->ok = ok;
+    box->terminal = (lg == 0 && legal_moves(you, me) == 0) ? 1 : 0;                          // :249-264
+    box->winner = winner(me, you);                                                           // :266-282
+    box->self_count = popc64(me); box->opp_count = popc64(you);                              // :292-298
+    __threadfence_system();
+    *reinterpret_cast<volatile uint64_t*>(&box->seq) = seq;
+}
+
 // float32 [n,3,8,8]; one thread writes 4 consecutive squares of one plane (16-byte store)
 __global__ void __launch_bounds__(kBlock) k_tensor_input(const uint64_t* __restrict__ me, const uint64_t* __restrict__ you,
                                                          float4* __restrict__ out, int64_t n)
@@ -323,6 +340,27 @@ int oth_terminal_winner(oth_ctx* ctx, const uint64_t* self_b, const uint64_t* op
     k_terminal_winner<<<grid_for(n, kBlock, ctx->sm_count), kBlock, 0, ctx->stream>>>(a, b, t, w, c, n);
     LAUNCH_CHECK(ctx);
     return st.finish();
+}
+
+int oth_board_step(oth_ctx* ctx, uint64_t self_b, uint64_t opp_b, int32_t move_count, int32_t action, oth_board_state* out)
+{
+    OTH_REQUIRE(ctx && out, OTH_ERR_ARG, "oth_board_step: NULL argument");
+    OTH_CHECK_CUDA(cudaSetDevice(ctx->device));
+    const uint64_t seq = ++ctx->mailbox_seq;
+    k_board_step<<<1, 32, 0, ctx->stream>>>(self_b, opp_b, move_count, action, seq, ctx->mailbox_dev);
+    LAUNCH_CHECK(ctx);
+    // wait on the mailbox itself: a few microseconds sooner than cudaStreamSynchronize's wake-up; the stream sync
+    // remains the fallback so that a failed launch surfaces as an error instead of a spin
+    volatile uint64_t* flag = &ctx->mailbox->seq;
+    for (int spin = 0; spin < 200000 && *flag != seq; ++spin) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    if (*flag != seq) OTH_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    OTH_REQUIRE(*flag == seq, OTH_ERR_CUDA, "oth_board_step: the kernel did not deliver a result");
+    *out = *ctx->mailbox;
+    return OTH_OK;
 }
 
 int oth_tensor_input(oth_ctx* ctx, const uint64_t* self_b, const uint64_t* opp_b, float* out, int64_t n, int mem)

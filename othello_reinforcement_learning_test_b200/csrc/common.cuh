@@ -51,6 +51,10 @@ struct oth_ctx {
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;       // kernels launched through this context (bench: gpu_launches)
     oth::KernelTimer timer;
+    // single-board mailbox (oth_board_step): page-locked, mapped into the device; the kernel writes the result there
+    oth_board_state* mailbox = nullptr;       // host address
+    oth_board_state* mailbox_dev = nullptr;   // device alias of the same memory
+    uint64_t mailbox_seq = 0;
 };
 
 namespace oth {

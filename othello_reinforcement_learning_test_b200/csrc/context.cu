@@ -1,5 +1,6 @@
 // context.cu -- library context, error text, host staging.
 #include <stdarg.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -78,6 +79,10 @@ int oth_ctx_create(int device, oth_ctx** out)
     c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; oth::set_error("stream create: %s", cudaGetErrorString(e)); return OTH_ERR_CUDA; }
+    e = cudaHostAlloc((void**)&c->mailbox, sizeof(oth_board_state), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&c->mailbox_dev, c->mailbox, 0);
+    if (e != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; oth::set_error("mailbox alloc: %s", cudaGetErrorString(e)); return OTH_ERR_CUDA; }
+    memset(c->mailbox, 0, sizeof(oth_board_state));
     *out = c;
     return OTH_OK;
 }
@@ -90,6 +95,7 @@ int oth_ctx_destroy(oth_ctx* ctx)
     for (int c = 0; c < oth::kTimerCats; ++c)
         for (cudaEvent_t e : ctx->timer.pool[c]) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
     delete ctx;
     return OTH_OK;
 }

@@ -19,32 +19,57 @@ struct ReplayHost {
     oth_sample* ring = nullptr;
     int64_t* d_idx = nullptr; int64_t idx_cap = 0;
     double* d_stats = nullptr;
+    int32_t* d_bad = nullptr;                     // set by the gather kernel when a device-side index was out of range
 };
+
+// Dihedral image t = 2*k + flip of the board, in the order of OthelloBitboard.get_symmetries (bitboard.pyx:338-370):
+// np.rot90(planes, k, axes=(1, 2)) then np.flip(axis=2) when flip.  Returns the SOURCE square whose content lands on
+// destination square d: rot90 once is out[i][j] = in[j][7 - i]; the flip is out[i][j] = in[i][7 - j].
+__host__ __device__ __forceinline__ int sym_source_square(int d, int t)
+{
+    int i = d >> 3, j = d & 7;
+    if (t & 1) j = 7 - j;
+    for (int k = t >> 1; k > 0; --k) { const int ni = j, nj = 7 - i; i = ni; j = nj; }
+    return (i << 3) | j;
+}
 
 // one warp per sample: 168 B in, 192 + 65 + 1 floats out
 __global__ void __launch_bounds__(256)
-k_replay_gather(const oth_sample* __restrict__ ring, int64_t capacity, int64_t head, const int64_t* __restrict__ idx, int64_t n,
-                float* __restrict__ states, float* __restrict__ policies, float* __restrict__ values)
+k_replay_gather(const oth_sample* __restrict__ ring, int64_t capacity, int64_t head, int64_t size, const int64_t* __restrict__ idx,
+                const uint8_t* __restrict__ sym, int64_t n, float* __restrict__ states, float* __restrict__ policies,
+                float* __restrict__ values, int32_t* __restrict__ bad)
 {
     const int64_t i = blockIdx.x * 8LL + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (i >= n) return;
-    const oth_sample* s = ring + (head + idx[i]) % capacity;
+    int64_t li = idx[i];
+    if (li < 0 || li >= size) {                                        // never read a stale ring entry: flag it, use entry 0
+        if (lane == 0) atomicExch(bad, 1);
+        li = 0;
+    }
+    const oth_sample* s = ring + (head + li) % capacity;
     const uint64_t planes[3] = {s->self_b, s->opp_b, s->legal};
+    const int t = sym ? (sym[i] & 7) : 0;                              // dihedral image (0 = identity)
+    const int src0 = sym_source_square(lane, t), src1 = sym_source_square(lane + 32, t);
     float* st = states + i * 192;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         const int e = k * 32 + lane;                                   // element of the [3][64] planes
-        st[e] = (float)((planes[e >> 6] >> (e & 63)) & 1ULL);          // get_tensor_input layout (bitboard.pyx:300-323)
+        const int sq = (k & 1) ? src1 : src0;                          // the 8 images are bit permutations of the packed planes
+        st[e] = (float)((planes[e >> 6] >> sq) & 1ULL);                // get_tensor_input layout (bitboard.pyx:300-323)
     }
     // policy = counts / counts.sum() in float32 (node.py:177-180); counts are small integers, the sum is exact
     int part = 0;
     for (int j = lane; j < OTH_ACTIONS; j += 32) part += s->visits[j];
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
     const float total = (float)part;
-    for (int j = lane; j < OTH_ACTIONS; j += 32)
-        policies[i * OTH_ACTIONS + j] = part > 0 ? __fdiv_rn((float)s->visits[j], total) : 0.f;
-    if (lane == 0) values[i] = (float)s->value;
+    float* po = policies + i * OTH_ACTIONS;
+    po[lane] = part > 0 ? __fdiv_rn((float)s->visits[src0], total) : 0.f;
+    po[lane + 32] = part > 0 ? __fdiv_rn((float)s->visits[src1], total) : 0.f;
+    if (lane == 0) {
+        po[64] = part > 0 ? __fdiv_rn((float)s->visits[64], total) : 0.f;     // the pass probability is carried (bitboard.pyx:365)
+        values[i] = (float)s->value;
+    }
 }
 
 __global__ void k_replay_stats(const oth_sample* __restrict__ ring, int64_t n, double* __restrict__ out)
@@ -76,6 +101,8 @@ int oth_replay_create(oth_ctx* ctx, int64_t max_size, oth_replay** out)
     r->ctx = ctx; r->capacity = max_size;
     cudaError_t e = cudaMalloc((void**)&r->ring, (size_t)max_size * sizeof(oth_sample));
     if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_stats, 2 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_bad, sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(r->d_bad, 0, sizeof(int32_t), ctx->stream);
     if (e != cudaSuccess) { set_error("oth_replay_create: %s", cudaGetErrorString(e)); cudaFree(r->ring); delete r; return OTH_ERR_CUDA; }
     *out = r;
     return OTH_OK;
@@ -86,7 +113,7 @@ int oth_replay_destroy(oth_replay* r)
     if (!r) return OTH_OK;
     cudaSetDevice(r->ctx->device);
     cudaStreamSynchronize(r->ctx->stream);
-    cudaFree(r->ring); cudaFree(r->d_idx); cudaFree(r->d_stats);
+    cudaFree(r->ring); cudaFree(r->d_idx); cudaFree(r->d_stats); cudaFree(r->d_bad);
     delete r;
     return OTH_OK;
 }
@@ -120,21 +147,53 @@ int oth_replay_add(oth_replay* r, const oth_sample* samples, int64_t n, int mem)
     return OTH_OK;
 }
 
-// gather + expand the samples at logical indices idx[0..n) (0 = oldest) into the trainer's tensors
-int oth_replay_gather(oth_replay* r, const int64_t* idx, int64_t n, float* states, float* policies, float* values, int mem)
+// gather + expand the samples at logical indices idx[0..n) (0 = oldest) into the trainer's tensors; sym (optional, one
+// byte per sample, 0..7) picks a dihedral image of the sample in get_symmetries' order (bitboard.pyx:338-370)
+static int replay_gather(oth_replay* r, const int64_t* idx, const uint8_t* sym, int64_t n, float* states, float* policies,
+                         float* values, int mem)
 {
     OTH_REQUIRE(r && idx && states && policies && values && n > 0, OTH_ERR_ARG, "oth_replay_gather: bad argument");
     oth_ctx* ctx = r->ctx;
     OTH_CHECK_CUDA(cudaSetDevice(ctx->device));
     Staged st(ctx, mem);
     const int64_t* di = st.in(idx, n);
+    const uint8_t* dsym = sym ? st.in(sym, n) : nullptr;
     float* ds = st.out(states, n * 192); float* dp = st.out(policies, n * OTH_ACTIONS); float* dv = st.out(values, n);
     if (st.failed) return OTH_ERR_CUDA;
     if (mem == OTH_MEM_HOST) for (int64_t i = 0; i < n; ++i) OTH_REQUIRE(idx[i] >= 0 && idx[i] < r->size, OTH_ERR_ARG, "oth_replay_gather: index %lld out of range (size %lld)", (long long)idx[i], (long long)r->size);
-    k_replay_gather<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(r->ring, r->capacity, r->head, di, n, ds, dp, dv);
+    k_replay_gather<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(r->ring, r->capacity, r->head, r->size, di, dsym, n, ds, dp, dv, r->d_bad);
     ctx->launches++;
     OTH_CHECK_CUDA(cudaGetLastError());
     return st.finish();
+}
+
+int oth_replay_gather(oth_replay* r, const int64_t* idx, int64_t n, float* states, float* policies, float* values, int mem)
+{
+    return replay_gather(r, idx, nullptr, n, states, policies, values, mem);
+}
+
+int oth_replay_gather_sym(oth_replay* r, const int64_t* idx, const uint8_t* sym, int64_t n, float* states, float* policies,
+                          float* values, int mem)
+{
+    OTH_REQUIRE(sym, OTH_ERR_ARG, "oth_replay_gather_sym: sym is NULL");
+    return replay_gather(r, idx, sym, n, states, policies, values, mem);
+}
+
+// Device-side index check of the gathers issued with OTH_MEM_DEVICE so far (their indices cannot be validated on the
+// host): synchronises, returns OTH_ERR_ARG once if any index was outside [0, size) and clears the flag.
+int oth_replay_check(oth_replay* r)
+{
+    OTH_REQUIRE(r, OTH_ERR_ARG, "oth_replay_check: NULL handle");
+    OTH_CHECK_CUDA(cudaSetDevice(r->ctx->device));
+    int32_t bad = 0;
+    OTH_CHECK_CUDA(cudaMemcpyAsync(&bad, r->d_bad, sizeof bad, cudaMemcpyDeviceToHost, r->ctx->stream));
+    OTH_CHECK_CUDA(cudaStreamSynchronize(r->ctx->stream));
+    if (bad) {
+        OTH_CHECK_CUDA(cudaMemsetAsync(r->d_bad, 0, sizeof bad, r->ctx->stream));
+        set_error("oth_replay_gather: a device-side index was outside [0, %lld)", (long long)r->size);
+        return OTH_ERR_ARG;
+    }
+    return OTH_OK;
 }
 
 // get_statistics (buffer.py:102-123): mean and (population) std of the value labels

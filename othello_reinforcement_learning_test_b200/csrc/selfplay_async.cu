@@ -16,6 +16,7 @@
 //
 // The table is only READ in k_as_advance and only WRITTEN in k_tree_expand, which are different kernels: no torn entries.
 #include <math.h>
+#include <stdlib.h>
 
 #include "selfplay.cuh"
 
@@ -25,6 +26,8 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kLanes = 8;                       // lanes per slot (as k_tree_select / k_tree_expand)
 constexpr int kAsBlock = 64;                    // 2 warps = 8 slots per block: small campaigns spread over many SMs
 constexpr int kSlotsPerBlock = kAsBlock / kLanes;
+
+constexpr int kAsyncStepsPerTick = 6;           // simulations / moves one slot may complete per launch (tuned on B200)
 
 constexpr int kEvalPerGame = 0;                 // evaluator indexed by game (hash-net): no batch slot
 constexpr int kEvalDirect = 1;                  // cache off: a batch slot straight away
@@ -318,7 +321,10 @@ int SelfPlayHost::run_async(NetHost* net, int64_t num_episodes)
     AsyncParams p{};
     p.num_episodes = num_episodes;
     p.sims = cfg.num_simulations; p.threshold = cfg.temperature_threshold;
-    p.max_steps = 2 * (cfg.num_simulations + 2);         // at most about two plies' worth of hits per launch: bounds the tail
+    // A launch lasts as long as its longest chain of cache hits; the network launch that follows waits for it.  Chains are
+    // short (about half the leaves miss), so a small cap costs few extra ticks and keeps the tail bounded.
+    p.max_steps = kAsyncStepsPerTick;
+    if (const char* e = getenv("OTH_ASYNC_MAX_STEPS")) { const int v = atoi(e); if (v > 0) p.max_steps = v; }
     p.eval_mode = hash ? kEvalPerGame : (use_cache ? kEvalCached : kEvalDirect);
     p.c32 = (float)cfg.c_puct; p.flags = cfg.flags; p.seed = run_seed;
     TreeDev view = s.t;
@@ -349,6 +355,7 @@ int SelfPlayHost::run_async(NetHost* net, int64_t num_episodes)
             OTH_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
             OTH_REQUIRE(h_counters[5] == 0, OTH_ERR_CAPACITY, "oth_selfplay_run: trajectory buffer overflow");
             if ((int64_t)h_counters[1] >= num_episodes) break;
+            if ((tick + 1) % (16 * check_every) == 0 && (rc = s.check_overflow())) return rc;   // a full edge pool would stall its slot forever
         }
     }
     moves_played += (uint64_t)h_counters[6];

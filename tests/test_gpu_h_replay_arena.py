@@ -125,3 +125,93 @@ def test_arena_play_game_is_one_game_of_a_match(ctx, capsys):
     pkg.Arena(verbose=True).play_matches(a, b, num_games=2)
     out = capsys.readouterr().out
     assert "Match Summary" in out and "Total Games: 2" in out and "Average Moves:" in out
+
+
+def test_device_side_symmetry_augmentation_equals_the_reference_get_symmetries(golden_symmetry):
+    """the 8 dihedral images as bit permutations of the packed records inside the gather kernel, against
+    what the compiled reference's get_symmetries (bitboard.pyx:338-370) returned (tests/golden/symmetry_ref.npz)."""
+    import torch
+    import othello_reinforcement_learning_test_b200 as pkg
+    from othello_reinforcement_learning_test_b200 import _lib
+    g = golden_symmetry
+    n = g["self_b"].size
+    rec = np.zeros(n, _lib.SAMPLE_DTYPE)
+    rec["self_b"], rec["opp_b"] = g["self_b"], g["opp_b"]
+    rec["legal"] = cref.legal_batch(g["self_b"], g["opp_b"])
+    rec["visits"][:, :64] = np.arange(1, 65, dtype=np.uint16)[None, :]        # a distinct count on every square
+    rec["visits"][:, 64] = 100
+    rec["value"] = np.where(np.arange(n) % 2 == 0, 1, -1)
+    total = np.float32(rec["visits"][0].astype(np.int64).sum())
+    buf = pkg.ReplayBuffer(max_size=n)
+    buf.add_packed(rec)
+    w8 = (1 << np.arange(64, dtype=np.uint64))
+    for t in range(8):
+        st, po, va = buf.gather(np.arange(n), np.full(n, t, np.uint8))
+        bits = ((st.reshape(n, 3, 64) > 0.5).astype(np.uint64) * w8).sum(axis=2, dtype=np.uint64)
+        assert np.array_equal(bits, g["planes"][:, t]), t                      # planes: bit-exact with the reference's images
+        for i in range(n):
+            # where did the reference move square s's probability?  pi has distinct values, so the permutation is readable
+            src = np.array([int(np.flatnonzero(g["pi"][i, :64] == v)[0]) for v in g["policy"][i, t, :64]])
+            assert np.array_equal(po[i, :64], (src + 1).astype(np.float32) / total), (t, i)
+            assert po[i, 64] == np.float32(100) / total and g["policy"][i, t, 64] == g["pi"][i, 64]
+        assert np.array_equal(va[:, 0], rec["value"].astype(np.float32))
+    # identity image == plain gather; device path (CUDA tensors) == host path
+    a = buf.gather(np.arange(n), np.zeros(n, np.uint8)); b = buf.gather(np.arange(n))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    random.seed(3)
+    ts, tp, tv = buf.sample_torch(32, augment=True)
+    assert ts.shape == (32, 3, 8, 8) and torch.allclose(tp.sum(dim=1), torch.ones(32, device=tp.device), atol=1e-6)
+    assert ((ts[:, 0] + ts[:, 1]) <= 1).all()                                  # still a board: no square owned twice
+    buf.check()
+    # a bad device-side index is flagged instead of reading a stale ring slot (ADVICE r1)
+    from othello_reinforcement_learning_test_b200._lib import MEM_DEVICE, check, ptr
+    idx = torch.tensor([0, n + 5], dtype=torch.int64, device="cuda")
+    o1 = torch.empty((2, 3, 8, 8), device="cuda"); o2 = torch.empty((2, 65), device="cuda"); o3 = torch.empty((2, 1), device="cuda")
+    torch.cuda.synchronize()
+    check(buf.ctx.lib.oth_replay_gather(buf.handle, ptr(idx), 2, ptr(o1), ptr(o2), ptr(o3), MEM_DEVICE))
+    with pytest.raises(pkg.OthelloB200Error):
+        buf.check()
+    buf.check()                                                                 # the flag is cleared by the report
+
+
+def test_single_board_step_is_one_call_and_matches_the_oracle(golden_games):
+    """oth_board_step: make_move + legal mask + terminal + winner + counts of the position reached in ONE launch, against
+    the oracle on reference game positions (accepts, rejects, passes, terminal positions); latency is printed."""
+    import ctypes as C
+    import time
+    import othello_reinforcement_learning_test_b200 as pkg
+    from othello_reinforcement_learning_test_b200 import _lib
+    ctx = pkg.Context.default(0)
+    g = golden_games
+    rng = np.random.default_rng(12)
+    pick = rng.choice(g["self_b"].size, 400, replace=False)
+    st = _lib.BoardState()
+    for i in pick:
+        s, o, mc = int(g["self_b"][i]), int(g["opp_b"][i]), int(g["move_count"][i])
+        for a in (_lib.ACTION_NONE, int(g["action"][i]), int(rng.integers(0, 65)), -1, 99):
+            launches = ctx.launch_count
+            _lib.check(ctx.lib.oth_board_step(ctx.handle, s, o, mc, a, C.byref(st)))
+            assert ctx.launch_count == launches + 1
+            if a == _lib.ACTION_NONE:
+                ok, s2, o2, mc2 = True, s, o, mc
+            else:
+                ok, s2, o2, mc2 = cref.make_move(s, o, mc, a)
+                if not ok:
+                    s2, o2, mc2 = s, o, mc
+            assert (bool(st.ok), int(st.self_b), int(st.opp_b), int(st.move_count)) == (bool(ok), s2, o2, mc2), (i, a)
+            assert int(st.legal) == cref.legal(s2, o2) and bool(st.terminal) == cref.is_terminal(s2, o2)
+            assert int(st.winner) == cref.winner(s2, o2)
+            assert (int(st.self_count), int(st.opp_count)) == (bin(s2).count("1"), bin(o2).count("1"))
+    # the board class: one launch per move, everything else answered from that result
+    b = pkg.OthelloBitboard()
+    b.get_legal_moves()
+    n_moves, t0, l0 = 0, time.perf_counter(), ctx.launch_count
+    while not b.is_terminal():
+        lm = b.get_legal_moves()
+        assert b.make_move(lm[len(lm) // 2])
+        b.get_winner(); b.get_stone_counts(); b.get_tensor_input()
+        n_moves += 1
+    dt = time.perf_counter() - t0
+    assert ctx.launch_count - l0 == n_moves
+    print(f"\\nsingle-board path: {1e6 * dt / n_moves:.1f} us per move incl. is_terminal/get_legal_moves/get_winner/get_stone_counts/"
+          f"get_tensor_input ({n_moves} moves, 1 launch each)")
