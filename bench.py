@@ -602,7 +602,7 @@ def main():
     ap.add_argument("--no-eval-cache", action="store_true", help="evaluate every leaf with the network (no position cache / dedup)")
     ap.add_argument("--no-sharing", action="store_true", help="every slot runs its own search (identical roots do not share one)")
     ap.add_argument("--schedule", default="auto", choices=["auto", "lockstep", "async"],
-                    help="lockstep: 1 + sims network launches per ply; async: run-until-miss; auto: async up to 32,768 slots")
+                    help="lockstep: 1 + sims network launches per ply; async: run-until-miss; auto: async up to 8,192 slots")
     ap.add_argument("--warmup-games", type=int, default=18944, help="games per warm-up campaign (the timed steps are full campaigns)")
     ap.add_argument("--no-legs", action="store_true", help="skip the secondary legs (BASELINE configs 2/3-literal/4, decomposition)")
     ap.add_argument("--leg-deadline", type=float, default=600.0, help="secondary legs are skipped once the run is older than this (s)")

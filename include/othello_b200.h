@@ -205,7 +205,7 @@ typedef struct {
  *   ASYNC:    run-until-miss -- every slot keeps simulating, moving and starting its next search while its leaves hit
  *             the evaluation cache, and only stops when it needs the network: one launch per cache miss of the slowest
  *             slot instead of one per simulation.  Needs OTH_FLAG_EVAL_CACHE to pay off.
- *   AUTO:     ASYNC up to 32768 slots when the evaluation cache is on, LOCKSTEP otherwise. */
+ *   AUTO:     ASYNC up to 8192 slots when the evaluation cache is on, LOCKSTEP otherwise. */
 #define OTH_SCHEDULE_AUTO 0u
 #define OTH_SCHEDULE_LOCKSTEP 1u
 #define OTH_SCHEDULE_ASYNC 2u

@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libothello_b200.so")
+LIB_PATH = os.environ.get("OTH_LIB_PATH") or os.path.join(PKG_DIR, "libothello_b200.so")   # override: experiment builds
 
 OTH_OK = 0
 MEM_DEVICE, MEM_HOST = 0, 1

@@ -20,6 +20,8 @@
 //
 // Restates src/model/net.py:15-61,139-205 (eval mode, BN folded) -- numerics: bf16 operands,
 // fp32 accumulation in TMEM, bf16 activations between layers, fp32 heads.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "net_common.cuh"
 #include "net_host.cuh"
@@ -29,7 +31,24 @@
 namespace oth {
 namespace tc {
 
-constexpr int kStages = 6;
+#ifndef OTH_TC_STAGES
+#define OTH_TC_STAGES 6
+#endif
+#ifndef OTH_TC_COPY_SPLIT
+#define OTH_TC_COPY_SPLIT 1
+#endif
+constexpr int kStages = OTH_TC_STAGES;          // weight ring depth (8 KB slots); must divide 6 (stem) and 18 (one issue trip)
+constexpr int kCopySplit = OTH_TC_COPY_SPLIT;   // bulk copies per ring stage (experiment knob: requests in flight per byte)
+#ifndef OTH_TC_STAGE_GROUP
+#define OTH_TC_STAGE_GROUP 1
+#endif
+// Consecutive ring stages fetched by ONE bulk copy.  A bulk copy costs ~52 cycles + bytes / 35.4 B/clk on one SM (measured:
+// 2 KB copies 110 cycles, 8 KB copies 283), and with 8 KB per copy the weight stream (283 cycles per stage), not the tensor
+// core (256 cycles per stage for two tiles), sets the layer time.  Weights lie in streaming order, so a group is contiguous.
+constexpr int kGroup = OTH_TC_STAGE_GROUP;
+constexpr int kGroups = kStages / kGroup;       // barrier pairs: one bar_full / bar_empty per group
+static_assert(kStages % kGroup == 0 && 18 % kGroup == 0 && (kGroup == 1 || kGroup == 2), "stage groups: 1 or 2 stages per copy");
+static_assert(6 % kStages == 0 && 18 % kStages == 0, "ring depth must divide the stem's 6 stages and a trip's 18");
 
 template <int F>
 struct Cfg {
@@ -55,7 +74,7 @@ struct Cfg {
     static constexpr int offHeadW = offBias + 4 * F * 4;    // [3][F] fp32: policy 1x1 (2 channels) and value 1x1 weights
     static constexpr int kSmemBytes = offHeadW + 3 * F * 4;
     static_assert(2 * kStemTapBytes == kStageBytes, "stem stages reuse the trunk's ring slots");
-    static_assert(kStagesPerConv % (3 * kStages) == 0 && kSplits % 2 == 0, "issue loop: one trip = two splits = three ring rounds");
+    static_assert(kStagesPerConv % 18 == 0 && kSplits % 2 == 0, "issue loop: one trip = two splits = 18 stages = whole ring rounds");
     static_assert(offBias % 16 == 0 && offHeadW % 16 == 0, "bias / head-weight staging must be 16-byte aligned");
     static_assert(sizeof(HeadScratch) % 16 == 0, "HeadScratch must keep 16-byte alignment");
     static_assert(kRingSlotBytes % 128 == 0, "ring slots must stay 128-byte aligned");
@@ -94,7 +113,7 @@ __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off,
         for (int s = 0; s < 6; ++s) {                       // stage = (tap row dy = s/2 - 1, part): part 0 = taps dx -1,0; part 1 = dx +1
             constexpr int kTapUnits = C::kStemTapBytes >> 4;
             const int dy = s / 2, part = s % 2;
-            mbar_wait(&bar_full[s], round & 1);
+            if ((s % kStages) % kGroup == 0) mbar_wait(&bar_full[(s % kStages) / kGroup], (round + s / kStages) & 1);
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -103,17 +122,17 @@ __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off,
                     for (int k = 0; k < (part == 0 ? 2 : 1); ++k) {
                         const int tx = part == 0 ? k : 2;
                         const uint32_t a_u = a_row0 + (uint32_t)(tile * kTileUnits + (dy - 1) * 2 * kGroupUnits + (tx - 1));
-                        const uint32_t b_u = ring0 + (uint32_t)(s * kSlotUnits + k * kTapUnits);
+                        const uint32_t b_u = ring0 + (uint32_t)((s % kStages) * kSlotUnits + k * kTapUnits);
                         umma_bf16(d_col + (uint32_t)(tile * F), ((uint64_t)kAHi << 32) | a_u, ((uint64_t)kBHi << 32) | b_u, idesc,
                                   (s > 0 || k > 0) ? 1u : 0u);
                     }
                     if (s == 5) umma_commit(&bar_acc[tile]);
                 }
-                umma_commit(&bar_empty[s]);
+                if ((s % kStages) % kGroup == kGroup - 1) umma_commit(&bar_empty[(s % kStages) / kGroup]);
             }
             __syncwarp();
         }
-        ++round;
+        round += 6 / kStages;
     } else {
 #pragma unroll 1
         for (int trip = 0; trip < C::kSplits / 2; ++trip) {
@@ -125,7 +144,7 @@ __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off,
                     mbar_wait(&bar_act[0 * C::kSplits + trip * 2 + ql], act_phase); // tile 0
                     if (TILES > 1) mbar_wait(&bar_act[1 * C::kSplits + trip * 2 + ql], act_phase); // tile 1
                 }
-                mbar_wait(&bar_full[sl], (round + t / kStages) & 1);
+                if (sl % kGroup == 0) mbar_wait(&bar_full[sl / kGroup], (round + t / kStages) & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     const int shift = (tap / 3 - 1) * 2 * kGroupUnits + (tap % 3 - 1);
@@ -140,11 +159,11 @@ __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off,
                         }
                         if (t == 17 && trip == C::kSplits / 2 - 1) umma_commit(&bar_acc[tile]);   // this tile's accumulator is complete
                     }
-                    umma_commit(&bar_empty[sl]);                                    // slot free once both tiles have read it
+                    if (sl % kGroup == kGroup - 1) umma_commit(&bar_empty[sl / kGroup]);    // slot(s) free once both tiles have read them
                 }
                 __syncwarp();
             }
-            round += 3;
+            round += 18 / kStages;
         }
     }
 }
@@ -152,6 +171,11 @@ __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off,
 // TILES = 2: the throughput shape (4 boards per item, every weight stage feeds two tiles).  TILES = 1: the latency shape
 // for small batches (2 boards per item, twice as many CTAs busy, half the MMAs per layer on each): what a tick of a
 // 100-game campaign needs.  Same instructions per board in the same order, so outputs are identical bit for bit.
+// Tried and removed (B200, 10x128, 18,944 positions): thread-block clusters whose CTAs each fetch 1/CL of every ring stage
+// and multicast it to the cluster (cp.async.bulk ... multicast::cluster).  CL = 2: +2.4 % (+7.5 % with 16 KB copies), CL = 4:
+// half speed (cluster placement); a lone tile was not faster (the ~30 B/clk an SM's shared memory takes from bulk copies is
+// on the receiving side), and the outputs were not bit-identical to the unclustered kernel, which the evaluation cache
+// relies on.
 template <int F, int TILES>
 __global__ void __launch_bounds__(kThreads, 1)
 k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* __restrict__ opp_b, int64_t n,
@@ -172,6 +196,8 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
     const int n_layers = 1 + 2 * net.blocks;
     constexpr int kItemBoards = 2 * TILES;
     const int64_t n_items = (n + kItemBoards - 1) / kItemBoards;
+    // items this CTA walks: its own share, or (clusters) the same count for everybody
+    const int64_t my_rounds = n_items > blockIdx.x ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
@@ -205,7 +231,8 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
         uint32_t layer_count = 0;                         // accumulator buffer parity runs across items
         uint32_t it = 0;                                  // items done by this CTA
         const float ph_b0 = __ldg(net.ph_b), ph_b1 = __ldg(net.ph_b + 1), vh_b = __ldg(net.vh_b);
-        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        for (; it < my_rounds; ++it) {
+            const int64_t item = blockIdx.x + (int64_t)it * gridDim.x;
             named_bar_sync(kBarAll, TILES * 128);               // everybody is done reading the previous item's misc->s_self/opp
             if (threadIdx.x < kItemBoards) {
                 const int64_t b = item * kItemBoards + threadIdx.x;
@@ -280,17 +307,22 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
         if (lane == 0) {
             unsigned char* ring = smem + C::offRing;
             uint32_t cnt = 0;
-            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int64_t r = 0; r < my_rounds; ++r) {
                 const unsigned char* src = reinterpret_cast<const unsigned char*>(net.w_tc);
                 for (int layer = 0; layer < n_layers; ++layer) {
-                    const int stages = layer == 0 ? 6 : C::kStagesPerConv;
-                    for (int s = 0; s < stages; ++s, ++cnt) {
-                        // stem stages alternate two taps / one tap (taps dx = -1,0 then dx = +1 of a tap row)
-                        const uint32_t bytes = layer == 0 ? ((s & 1) ? C::kStemTapBytes : 2 * C::kStemTapBytes) : C::kStageBytes;
-                        const uint32_t slot = cnt % kStages, round = cnt / kStages;
+                    const int groups = (layer == 0 ? 6 : C::kStagesPerConv) / kGroup;
+                    for (int s = 0; s < groups; ++s, ++cnt) {
+                        // stem stages alternate two taps / one tap (taps dx = -1,0 then dx = +1 of a tap row): a stem stage
+                        // pair is 8 KB + 4 KB, contiguous, and the 4 KB land at the second slot's base like any second stage
+                        uint32_t bytes = kGroup * C::kStageBytes;
+                        if (layer == 0) bytes = kGroup == 2 ? 3 * C::kStemTapBytes : ((s & 1) ? C::kStemTapBytes : 2 * C::kStemTapBytes);
+                        const uint32_t slot = cnt % kGroups, round = cnt / kGroups;
                         mbar_wait(&bar_empty[slot], (round & 1) ^ 1);
                         mbar_expect_tx(&bar_full[slot], bytes);
-                        bulk_g2s(ring + slot * C::kRingSlotBytes, src, bytes, &bar_full[slot]);
+#pragma unroll
+                        for (int part = 0; part < kCopySplit; ++part)
+                            bulk_g2s(ring + slot * kGroup * C::kRingSlotBytes + part * (bytes / kCopySplit), src + part * (bytes / kCopySplit),
+                                     bytes / kCopySplit, &bar_full[slot]);
                         src += bytes;
                     }
                 }
@@ -306,11 +338,12 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
         uint32_t it = 0;
         // named barriers, not mbarriers (see the note at the accumulator wait): 128 epilogue threads + this warp
         named_bar_arrive(kBarHeadFree + tile, 160);                           // the scratch starts out free
-        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        for (; it < my_rounds; ++it) {
+            const int64_t item = blockIdx.x + (int64_t)it * gridDim.x;
             named_bar_sync(kBarHeadFull + tile, 160);
             heads_tail_warp(net, hs, misc->s_legal[it & 1] + 2 * tile, item * kItemBoards + 2 * tile, n, policy_out, value_out, out_kind, lane);
             __syncwarp();
-            if (item + gridDim.x < n_items) named_bar_arrive(kBarHeadFree + tile, 160);
+            if ((int64_t)it + 1 < my_rounds) named_bar_arrive(kBarHeadFree + tile, 160);
         }
     } else {
         // ===================== MMA issuer =====================
@@ -319,7 +352,7 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
         const uint32_t smem_base = smem_u32(smem);
         const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
         uint32_t round = 0, act_phase = 0, layer_count = 0;      // ring round: every layer uses whole ring rounds
-        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int64_t r = 0; r < my_rounds; ++r) {
             for (int layer = 0; layer < n_layers; ++layer, ++layer_count) {
                 const bool from_a = (layer == 0) || ((layer & 1) == 0);   // stem reads the input, conv2 reads h: both in A
                 const uint32_t in_off = from_a ? (uint32_t)C::offA : (uint32_t)C::offB;
@@ -364,9 +397,11 @@ int net_forward_tc(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, 
 {
     oth_ctx* ctx = net->ctx;
     OTH_REQUIRE(net_tc_supported(net->F), OTH_ERR_UNSUPPORTED, "tcgen05 engine supports num_filters 64 or 128 (got %d)", net->F);
-    // `n` is the host's upper bound of the batch (the device count n_dev can only be smaller): when even that bound fits one
-    // two-board item per SM, the one-tile shape halves the per-layer latency; otherwise the two-tile shape is the faster one.
-    const bool one_tile = (n + 1) / 2 <= ctx->sm_count;
+    // Tiles per CTA: two (4 boards per item) is the shape everything runs on.  The one-tile shape does not shorten a layer
+    // (measured: 10.2 k cycles per layer with one tile or two -- a layer lasts as long as its 288 KB of weights take to enter
+    // one SM's shared memory, ~30 B/clk); it is kept for experiments (OTH_TC_ONE_TILE=1, batches that fit one item per SM).
+    static const bool env_one_tile = getenv("OTH_TC_ONE_TILE") != nullptr;
+    const bool one_tile = env_one_tile && (n + 1) / 2 <= ctx->sm_count;
     int rc;
     if (net->F == 128) rc = one_tile ? launch_tc<128, 1>(net, self_b, opp_b, n, policy, value, out_kind, n_dev)
                                      : launch_tc<128, 2>(net, self_b, opp_b, n, policy, value, out_kind, n_dev);

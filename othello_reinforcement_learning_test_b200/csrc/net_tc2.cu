@@ -17,6 +17,10 @@
 //   bar_act[..]     leader only: one arrival per epilogue warp of the tile, 4 local + 4 remote, per 32-channel split
 // Both CTAs of a pair walk the same number of items; an index past the end is a dummy item (zero boards, no stores).
 //
+// Round 2 looked at this engine again as a LATENCY shape (one tile per CTA: half the weight bytes per SM for a small batch):
+// a layer takes 12.5-13.4 k cycles with one tile or two (the single-CTA kernel: 10.2 k), i.e. ~350 cycles per ring stage
+// whatever the MMA count, also with one relay lane per ring slot -- the pair's per-stage hand-shake, not bytes or MMAs, sets
+// its pace.  Not used for small batches either.
 // STATUS (measured on B200, 10x128, 18,944 positions/launch): bit-identical to net_tc.cu on every batch size tried, but
 // ~10 % slower kernel-only (1.46 vs 1.60-1.65 PFLOP/s): the pair's M=256 x N=128 x K=16 MMAs retire every ~78 cycles
 // instead of 64 (independent of ring depth 6/12 and of how the peer's "weights landed" reaches the leader), and the

@@ -8,7 +8,7 @@
 
 namespace oth {
 
-constexpr int64_t kAsyncAutoMaxSlots = 32768;   // OTH_SCHEDULE_AUTO: run-until-miss up to this many slots (measured crossover)
+constexpr int64_t kAsyncAutoMaxSlots = 8192;    // OTH_SCHEDULE_AUTO: run-until-miss up to this many slots (measured: +5..14 % up to 4,096 slots, even at 18,944)
 constexpr int kMaxPlies = 128;   // <= 60 placements + at most one pass between/around them
 static_assert(sizeof(oth_sample) == 168, "oth_sample layout is part of the C ABI");
 

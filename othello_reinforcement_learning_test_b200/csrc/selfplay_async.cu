@@ -27,7 +27,10 @@ constexpr int kLanes = 8;                       // lanes per slot (as k_tree_sel
 constexpr int kAsBlock = 64;                    // 2 warps = 8 slots per block: small campaigns spread over many SMs
 constexpr int kSlotsPerBlock = kAsBlock / kLanes;
 
-constexpr int kAsyncStepsPerTick = 6;           // simulations / moves one slot may complete per launch (tuned on B200)
+// Simulations / moves one slot may complete per launch.  A launch lasts as long as its longest chain of cache hits and
+// the network launch behind it waits; measured on B200 (10x128, 50 simulations): 100 slots -- cap 4: 186 games/s, 2: 177,
+// 12: 175, unbounded: 154 (lock-step: 178); 4,096 slots -- cap 2: 3,730, 4: 3,530, 12: 3,383 (lock-step: 3,407).
+__host__ inline int async_steps_per_tick(int64_t slots) { return slots < 2048 ? 4 : 2; }
 
 constexpr int kEvalPerGame = 0;                 // evaluator indexed by game (hash-net): no batch slot
 constexpr int kEvalDirect = 1;                  // cache off: a batch slot straight away
@@ -323,7 +326,7 @@ int SelfPlayHost::run_async(NetHost* net, int64_t num_episodes)
     p.sims = cfg.num_simulations; p.threshold = cfg.temperature_threshold;
     // A launch lasts as long as its longest chain of cache hits; the network launch that follows waits for it.  Chains are
     // short (about half the leaves miss), so a small cap costs few extra ticks and keeps the tail bounded.
-    p.max_steps = kAsyncStepsPerTick;
+    p.max_steps = async_steps_per_tick(d.slots);
     if (const char* e = getenv("OTH_ASYNC_MAX_STEPS")) { const int v = atoi(e); if (v > 0) p.max_steps = v; }
     p.eval_mode = hash ? kEvalPerGame : (use_cache ? kEvalCached : kEvalDirect);
     p.c32 = (float)cfg.c_puct; p.flags = cfg.flags; p.seed = run_seed;

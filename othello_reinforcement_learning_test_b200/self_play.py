@@ -154,7 +154,7 @@ class ParallelSelfPlayWorker:
         self.winner_black = winner_black
         self.share_searches = share_searches      # identical root positions run one search (same results)
         # "lockstep": 1 + sims network launches per ply; "async": run-until-miss (one launch per cache miss of the
-        # slowest slot); "auto": async up to 32,768 slots when the cache is on.  Same records either way.
+        # slowest slot); "auto": async up to 8,192 slots when the cache is on.  Same records either way.
         self.schedule = {"auto": _lib.SCHEDULE_AUTO, "lockstep": _lib.SCHEDULE_LOCKSTEP, "async": _lib.SCHEDULE_ASYNC}[schedule]
         self.seed = seed
         self.verbose = verbose
