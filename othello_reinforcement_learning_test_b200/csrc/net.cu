@@ -177,6 +177,36 @@ int NetHost::allocate()
     OTH_CHECK_CUDA(cudaMalloc((void**)&d_w_simt, w_simt_elems() * 4));
     const size_t small = (size_t)(1 + 2 * blocks) * F + 2 * F + 2 + 128 * 65 + 65 + F + 1 + 64 * 256 + 256 + 256 + 1 + 64;
     OTH_CHECK_CUDA(cudaMalloc((void**)&d_small, small * 4));
+    return make_weight_tensor_map();
+}
+
+// 2-D tensor map over d_w_tc: rows of 256 bytes (128 bf16); one box = one ring stage group of the trunk
+// (net_tc.cu: 32 input channels x F output channels of one tap = F / 4 rows, times the stage group).
+int NetHost::make_weight_tensor_map()
+{
+    tmap_ok = false;
+    if (!net_tc_supported(F)) return OTH_OK;
+    const size_t bytes = w_tc_elems() * 2;
+    if (bytes % 256) return OTH_OK;
+    tmap_box_rows = net_tc_stage_rows(F);
+    const cuuint64_t gdim[2] = {128, (cuuint64_t)(bytes / 256)};
+    const cuuint64_t gstride[1] = {256};
+    const cuuint32_t box[2] = {128, (cuuint32_t)tmap_box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    // the driver entry point is looked up at run time: the library must load on a box without libcuda (build check)
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+        cudaGetLastError();
+        return OTH_OK;                    // not fatal: the kernel falls back to 1-D bulk copies
+    }
+    const CUresult r = ((EncodeFn)fn)(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d_w_tc, gdim, gstride, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    tmap_ok = r == CUDA_SUCCESS;
     return OTH_OK;
 }
 

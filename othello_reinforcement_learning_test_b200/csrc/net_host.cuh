@@ -1,5 +1,7 @@
 // net_host.cuh -- host-side network object shared by net.cu, net_tc.cu, search.cu, selfplay.cu
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 #include "net_common.cuh"
 
@@ -15,17 +17,24 @@ struct NetHost {
     float* d_w_simt = nullptr;
     float* d_small = nullptr;
     NetDev dev{};
+    // tensor map over the tcgen05 weight buffer: 2-D view [rows][256 B], box = one ring stage (group), no swizzle --
+    // lets the trunk's weight stream go through cp.async.bulk.tensor (UTMALDG) instead of 1-D bulk copies
+    alignas(64) CUtensorMap tmap_w;
+    bool tmap_ok = false;
+    int tmap_box_rows = 0;
     uint64_t evals = 0;     // positions evaluated so far (bench bookkeeping)
 
     size_t w_tc_elems() const { return (size_t)9 * 16 * F + (size_t)2 * blocks * 9 * F * F; }
     size_t w_simt_elems() const { return (size_t)9 * 8 * F + (size_t)2 * blocks * 9 * F * F; }
     int allocate();
+    int make_weight_tensor_map();
     void release();
     int load(const float* flat, int64_t count);
 };
 
 int64_t net_param_count(int blocks, int F);
 bool net_tc_supported(int F);
+int net_tc_stage_rows(int F);      // 256-byte rows of one weight ring stage group of the tcgen05 trunk
 // all pointers are DEVICE pointers; asynchronous on net->ctx->stream
 // `n_dev` (optional, device): actual batch size decided on the GPU (<= n); the kernels read it themselves,
 // so a compacted leaf batch needs no host round trip.

@@ -179,7 +179,8 @@ __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off,
 template <int F, int TILES>
 __global__ void __launch_bounds__(kThreads, 1)
 k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* __restrict__ opp_b, int64_t n,
-         float* __restrict__ policy_out, float* __restrict__ value_out, int out_kind, const int32_t* __restrict__ n_dev)
+         float* __restrict__ policy_out, float* __restrict__ value_out, int out_kind, const int32_t* __restrict__ n_dev,
+         const __grid_constant__ CUtensorMap tmap_w, const int use_tmap)
 {
     if (n_dev) { const int64_t nd = *n_dev; n = nd < n ? nd : n; }      // batch size decided on the device
     using C = Cfg<F>;
@@ -319,10 +320,16 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
                         const uint32_t slot = cnt % kGroups, round = cnt / kGroups;
                         mbar_wait(&bar_empty[slot], (round & 1) ^ 1);
                         mbar_expect_tx(&bar_full[slot], bytes);
+                        if (use_tmap && layer > 0) {
+                            // trunk stages through the tensor map: one box = this stage (group), rows of 256 bytes
+                            tma_load_2d(ring + slot * kGroup * C::kRingSlotBytes, &tmap_w, 0,
+                                        (int32_t)((src - reinterpret_cast<const unsigned char*>(net.w_tc)) >> 8), &bar_full[slot]);
+                        } else {
 #pragma unroll
-                        for (int part = 0; part < kCopySplit; ++part)
-                            bulk_g2s(ring + slot * kGroup * C::kRingSlotBytes + part * (bytes / kCopySplit), src + part * (bytes / kCopySplit),
-                                     bytes / kCopySplit, &bar_full[slot]);
+                            for (int part = 0; part < kCopySplit; ++part)
+                                bulk_g2s(ring + slot * kGroup * C::kRingSlotBytes + part * (bytes / kCopySplit), src + part * (bytes / kCopySplit),
+                                         bytes / kCopySplit, &bar_full[slot]);
+                        }
                         src += bytes;
                     }
                 }
@@ -378,6 +385,8 @@ k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* 
 
 bool net_tc_supported(int F) { return F == 64 || F == 128; }
 
+int net_tc_stage_rows(int F) { return tc::kGroup * (F == 128 ? tc::Cfg<128>::kStageBytes : tc::Cfg<64>::kStageBytes) / 256; }
+
 template <int F, int TILES>
 static int launch_tc(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value, int out_kind,
                      const int32_t* n_dev)
@@ -388,7 +397,10 @@ static int launch_tc(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b
     int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
     if (grid < 1) grid = 1;
     OTH_CHECK_CUDA(cudaFuncSetAttribute(tc::k_net_tc<F, TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    tc::k_net_tc<F, TILES><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(net->dev, self_b, opp_b, n, policy, value, out_kind, n_dev);
+    static const bool env_tmap = getenv("OTH_TC_TMAP") != nullptr;
+    const int use_tmap = (env_tmap && net->tmap_ok) ? 1 : 0;
+    tc::k_net_tc<F, TILES><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(net->dev, self_b, opp_b, n, policy, value, out_kind, n_dev,
+                                                                            net->tmap_w, use_tmap);
     return OTH_OK;
 }
 

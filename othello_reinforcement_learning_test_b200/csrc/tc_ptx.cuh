@@ -48,6 +48,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// 2-D tiled TMA load (cp.async.bulk.tensor, SASS UTMALDG): box at (c0, c1) of the tensor map -> shared memory
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tensor_map, int32_t c0, int32_t c1, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(tensor_map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
