@@ -344,7 +344,7 @@ def run_b200(args):
         smp = worker.execute_episodes_packed(episodes, add_dirichlet_noise=True, reuse_buffer=True)   # campaign + D2H into pinned host memory
         if world > 1:                                                    # trajectories of every rank into the replay buffer,
             g0.record(stream)                                            # NCCL all-gather device to device
-            dptr, cnt = engine.samples_device()
+            dptr, cnt = worker._engine.samples_device()
             gathered, total_cnt = odist.all_gather_samples_device(dptr, cnt, dev, episodes=episodes)
             replay.clear()
             replay.add_device(gathered, total_cnt)

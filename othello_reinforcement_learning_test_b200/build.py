@@ -18,7 +18,7 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libothello_b200.so")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 
-SOURCES = ["context.cu", "board_ops.cu", "net.cu", "net_tc.cu", "net_tc2.cu", "umma_probe.cu", "search.cu", "search_wave.cu", "selfplay.cu", "selfplay_async.cu", "replay.cu"]
+SOURCES = ["context.cu", "board_ops.cu", "net.cu", "net_tc.cu", "net_tc_lat.cu", "net_tc2.cu", "umma_probe.cu", "search.cu", "search_wave.cu", "selfplay.cu", "selfplay_async.cu", "replay.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -180,19 +180,10 @@ int NetHost::allocate()
     return make_weight_tensor_map();
 }
 
-// 2-D tensor map over d_w_tc: rows of 256 bytes (128 bf16); one box = one ring stage group of the trunk
-// (net_tc.cu: 32 input channels x F output channels of one tap = F / 4 rows, times the stage group).
-int NetHost::make_weight_tensor_map()
+// 2-D tensor maps over d_w_tc: rows of 256 bytes (128 bf16); one box = one weight request of the kernel that uses the map
+// (k_net_tc: a ring stage group; k_net_lat: four / three stages of a conv).
+static bool encode_weight_map(CUtensorMap* map, void* base, size_t bytes, int box_rows)
 {
-    tmap_ok = false;
-    if (!net_tc_supported(F)) return OTH_OK;
-    const size_t bytes = w_tc_elems() * 2;
-    if (bytes % 256) return OTH_OK;
-    tmap_box_rows = net_tc_stage_rows(F);
-    const cuuint64_t gdim[2] = {128, (cuuint64_t)(bytes / 256)};
-    const cuuint64_t gstride[1] = {256};
-    const cuuint32_t box[2] = {128, (cuuint32_t)tmap_box_rows};
-    const cuuint32_t estr[2] = {1, 1};
     // the driver entry point is looked up at run time: the library must load on a box without libcuda (build check)
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -201,12 +192,24 @@ int NetHost::make_weight_tensor_map()
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
         cudaGetLastError();
-        return OTH_OK;                    // not fatal: the kernel falls back to 1-D bulk copies
+        return false;
     }
-    const CUresult r = ((EncodeFn)fn)(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d_w_tc, gdim, gstride, box, estr,
-                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    tmap_ok = r == CUDA_SUCCESS;
+    const cuuint64_t gdim[2] = {128, (cuuint64_t)(bytes / 256)};
+    const cuuint64_t gstride[1] = {256};
+    const cuuint32_t box[2] = {128, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return ((EncodeFn)fn)(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int NetHost::make_weight_tensor_map()
+{
+    tmap_ok = tmap_lat_ok = false;
+    if (!net_tc_supported(F)) return OTH_OK;
+    const size_t bytes = w_tc_elems() * 2;
+    if (bytes % 256) return OTH_OK;
+    tmap_ok = encode_weight_map(&tmap_w, d_w_tc, bytes, net_tc_stage_rows(F));          // not fatal: the kernels fall back to
+    tmap_lat_ok = encode_weight_map(&tmap_lat, d_w_tc, bytes, net_tc_lat_box_rows(F));  // 1-D bulk copies / the throughput shape
     return OTH_OK;
 }
 
@@ -449,7 +452,23 @@ int net_forward_device(NetHost* net, const uint64_t* self_b, const uint64_t* opp
                        int out_kind, const int32_t* n_dev)
 {
     TimedLaunch timed(net->ctx, 0);
-    if (net->engine == OTH_NET_ENGINE_TCGEN05) return net_forward_tc(net, self_b, opp_b, n, policy, value, out_kind, n_dev);
+    if (net->engine == OTH_NET_ENGINE_TCGEN05) {
+        // A small batch costs the network's LATENCY and runs on the latency shape (net_tc_lat.cu: one tile per CTA, tensor-map
+        // TMA weight stream, ~80 us instead of ~137 us for 10x128; identical bits), everything else on the throughput
+        // kernel.  When the batch size is only known on the device (n_dev: the compacted leaf batch of a search step) and the
+        // host's upper bound n exceeds the latency shape's range, BOTH kernels are launched and each one returns at once if
+        // the device count is not in its range -- an empty launch costs ~3 us, a device->host read-back would cost more.
+        const int64_t lat_max = net_tc_lat_max_positions(net);
+        if (lat_max > 0 && n > 0) {
+            if (n <= lat_max) return net_forward_tc_lat(net, self_b, opp_b, n, policy, value, out_kind, n_dev);
+            if (n_dev) {
+                int rc = net_forward_tc_lat(net, self_b, opp_b, n, policy, value, out_kind, n_dev);
+                if (rc) return rc;
+                return net_forward_tc(net, self_b, opp_b, n, policy, value, out_kind, n_dev, lat_max + 1);
+            }
+        }
+        return net_forward_tc(net, self_b, opp_b, n, policy, value, out_kind, n_dev);
+    }
     if (net->engine == OTH_NET_ENGINE_TCGEN05_PAIR) return net_forward_tc2(net, self_b, opp_b, n, policy, value, out_kind, n_dev);
     return net_forward_simt(net, self_b, opp_b, n, policy, value, out_kind, n_dev);
 }

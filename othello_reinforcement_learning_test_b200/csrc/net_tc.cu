@@ -180,9 +180,10 @@ template <int F, int TILES>
 __global__ void __launch_bounds__(kThreads, 1)
 k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* __restrict__ opp_b, int64_t n,
          float* __restrict__ policy_out, float* __restrict__ value_out, int out_kind, const int32_t* __restrict__ n_dev,
-         const __grid_constant__ CUtensorMap tmap_w, const int use_tmap)
+         const __grid_constant__ CUtensorMap tmap_w, const int use_tmap, const int64_t n_min)
 {
     if (n_dev) { const int64_t nd = *n_dev; n = nd < n ? nd : n; }      // batch size decided on the device
+    if (n < n_min) return;                                               // the latency shape (launched before) has taken this batch
     using C = Cfg<F>;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::offBars);
@@ -389,7 +390,7 @@ int net_tc_stage_rows(int F) { return tc::kGroup * (F == 128 ? tc::Cfg<128>::kSt
 
 template <int F, int TILES>
 static int launch_tc(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value, int out_kind,
-                     const int32_t* n_dev)
+                     const int32_t* n_dev, int64_t n_min)
 {
     using C = tc::Cfg<F>;
     oth_ctx* ctx = net->ctx;
@@ -400,12 +401,12 @@ static int launch_tc(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b
     static const bool env_tmap = getenv("OTH_TC_TMAP") != nullptr;
     const int use_tmap = (env_tmap && net->tmap_ok) ? 1 : 0;
     tc::k_net_tc<F, TILES><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(net->dev, self_b, opp_b, n, policy, value, out_kind, n_dev,
-                                                                            net->tmap_w, use_tmap);
+                                                                            net->tmap_w, use_tmap, n_min);
     return OTH_OK;
 }
 
 int net_forward_tc(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, int64_t n, float* policy, float* value,
-                   int out_kind, const int32_t* n_dev)
+                   int out_kind, const int32_t* n_dev, int64_t n_min)
 {
     oth_ctx* ctx = net->ctx;
     OTH_REQUIRE(net_tc_supported(net->F), OTH_ERR_UNSUPPORTED, "tcgen05 engine supports num_filters 64 or 128 (got %d)", net->F);
@@ -415,10 +416,10 @@ int net_forward_tc(NetHost* net, const uint64_t* self_b, const uint64_t* opp_b, 
     static const bool env_one_tile = getenv("OTH_TC_ONE_TILE") != nullptr;
     const bool one_tile = env_one_tile && (n + 1) / 2 <= ctx->sm_count;
     int rc;
-    if (net->F == 128) rc = one_tile ? launch_tc<128, 1>(net, self_b, opp_b, n, policy, value, out_kind, n_dev)
-                                     : launch_tc<128, 2>(net, self_b, opp_b, n, policy, value, out_kind, n_dev);
-    else rc = one_tile ? launch_tc<64, 1>(net, self_b, opp_b, n, policy, value, out_kind, n_dev)
-                       : launch_tc<64, 2>(net, self_b, opp_b, n, policy, value, out_kind, n_dev);
+    if (net->F == 128) rc = one_tile ? launch_tc<128, 1>(net, self_b, opp_b, n, policy, value, out_kind, n_dev, n_min)
+                                     : launch_tc<128, 2>(net, self_b, opp_b, n, policy, value, out_kind, n_dev, n_min);
+    else rc = one_tile ? launch_tc<64, 1>(net, self_b, opp_b, n, policy, value, out_kind, n_dev, n_min)
+                       : launch_tc<64, 2>(net, self_b, opp_b, n, policy, value, out_kind, n_dev, n_min);
     if (rc) return rc;
     ctx->launches++;
     OTH_CHECK_CUDA(cudaGetLastError());

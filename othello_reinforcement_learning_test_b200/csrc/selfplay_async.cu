@@ -58,30 +58,55 @@ __global__ void __launch_bounds__(256) k_as_begin(SelfPlayDev d, TreeDev t)
     t.pending[g] = 0; t.eval_slot[g] = -1;
 }
 
-__device__ __forceinline__ void backup(Edge* E, const int32_t* path, int depth, double v)
+// One step of the path a descent took: the edge and the statistics it had when it was chosen.  Kept in shared memory so
+// that the backup is a set of independent stores (no re-load of the edges, lanes take one level each).
+struct PathStep {
+    double w;
+    int32_t idx, n;
+};
+constexpr int kPathSmem = 64;                   // levels kept in shared memory per slot (tree depth stays far below: <= 7 measured)
+
+// mcts.py:152-168: value v at the leaf's edge, sign flip per level going up, the root untouched.  Level d is handled by
+// lane d (mod 8): E[idx].n = n + 1, E[idx].w = w + (+-v) -- the same two operations `child.update(value)` performs.
+__device__ __forceinline__ void backup_from_smem(Edge* E, const PathStep* ps, int depth, double v, int sub)
 {
-    for (int dd = depth - 1; dd >= 0; --dd) {               // mcts.py:152-168: sign flip per level, root untouched
-        Edge* ed = E + path[dd];
-        ed->n += 1;
-        ed->w += v;
-        v = -v;
+    for (int dd = sub; dd < depth; dd += kLanes) {
+        const PathStep st = ps[dd];
+        Edge* ed = E + st.idx;
+        ed->n = st.n + 1;
+        ed->w = st.w + (((depth - 1 - dd) & 1) ? -v : v);
     }
 }
 
+// Per-slot state lives in registers for the whole launch (all 8 lanes hold the same values) and is written back once;
+// a step then costs the descent's dependent loads (one 24-byte record per level), the table probe and, on a hit, the
+// priors row -- not the two dozen dependent global round trips of a load-modify-store per counter and per backup level.
 __global__ void __launch_bounds__(kAsBlock) k_as_advance(SelfPlayDev d, TreeDev t, AsyncParams p)
 {
+    __shared__ PathStep s_path[kSlotsPerBlock][kPathSmem];
     const int lane = threadIdx.x & 31, sub = lane & (kLanes - 1);
-    const int64_t g = blockIdx.x * (int64_t)kSlotsPerBlock + (threadIdx.x / kLanes);
+    const int grp_in_block = threadIdx.x / kLanes;
+    const int64_t g = blockIdx.x * (int64_t)kSlotsPerBlock + grp_in_block;
     const int64_t gs = g < d.slots ? g : 0;
     bool run = g < d.slots && d.active[gs] && !t.pending[gs];
     Edge* E = t.edges + gs * (int64_t)t.edge_cap;
-    int32_t* path = t.path + gs * t.path_cap;
+    PathStep* ps = s_path[grp_in_block];
+    const int path_cap = t.path_cap < kPathSmem ? t.path_cap : kPathSmem;
+
+    // slot state
+    int rc = 0, sd = 0, n_edges = 0, n_nodes = 0, n_evals = 0, ply = 0, game = 0;
+    uint64_t root_me = 0ULL, root_you = 0ULL;
+    unsigned hits = 0;
+    bool dirty = false;
+    if (run) {
+        rc = t.root_count[gs]; sd = t.sims_done[gs]; n_edges = t.n_edges[gs]; n_nodes = t.n_nodes[gs]; n_evals = t.n_evals[gs];
+        root_me = t.root_self[gs]; root_you = t.root_opp[gs];
+        ply = d.move_count[gs]; game = d.game_id[gs];
+    }
 
     for (int step = 0; step < p.max_steps; ++step) {
         if (!__any_sync(kFull, run)) break;
-        int rc = 0, sd = 0;
-        uint64_t me = 0ULL, you = 0ULL;
-        if (run) { rc = t.root_count[gs]; sd = t.sims_done[gs]; me = t.root_self[gs]; you = t.root_opp[gs]; }
+        uint64_t me = root_me, you = root_you;
         const bool do_move = run && rc > 0 && sd >= p.sims;          // the search of this ply is complete
         const bool do_sim = run && !do_move;                         // root request (rc == 0) or one simulation
 
@@ -93,7 +118,7 @@ __global__ void __launch_bounds__(kAsBlock) k_as_advance(SelfPlayDev d, TreeDev 
             bool descending = cnt > 0;
             while (__any_sync(kFull, descending)) {
                 const double root_of_n = sqrt((double)parent_n);
-                double best = -INFINITY;
+                double best = -INFINITY, b_w = 0.0;
                 int best_e = 0x7FFFFFFF, b_n = 0, b_first = kEdgeLeaf, b_cnt = 0, b_act = 0;
                 if (descending) {
                     for (int k = sub; k < cnt; k += kLanes) {
@@ -104,7 +129,7 @@ __global__ void __launch_bounds__(kAsBlock) k_as_advance(SelfPlayDev d, TreeDev 
                         const double u = __ddiv_rn(__dmul_rn((double)cp, root_of_n), (double)(1 + ed.n));
                         const double sc = __dadd_rn(q, u);
                         if (sc > best) {                                                // strict >: first maximum wins
-                            best = sc; best_e = first + k; b_n = ed.n; b_first = ed.child_first; b_cnt = ed.child_count; b_act = ed.action;
+                            best = sc; best_e = first + k; b_n = ed.n; b_w = ed.w; b_first = ed.child_first; b_cnt = ed.child_count; b_act = ed.action;
                         }
                     }
                 }
@@ -117,20 +142,22 @@ __global__ void __launch_bounds__(kAsBlock) k_as_advance(SelfPlayDev d, TreeDev 
                     if (os > best || (os == best && oe < best_e)) { best = os; best_e = oe; win_lane = ol; }
                 }
                 const int w_n = __shfl_sync(kFull, b_n, win_lane, kLanes);
+                const double w_w = __shfl_sync(kFull, b_w, win_lane, kLanes);
                 const int w_first = __shfl_sync(kFull, b_first, win_lane, kLanes);
                 const int w_cnt = __shfl_sync(kFull, b_cnt, win_lane, kLanes);
                 const int w_act = __shfl_sync(kFull, b_act, win_lane, kLanes);
                 if (descending) {
                     parent_n = w_n;
                     cnt = w_cnt;
-                    if (sub == 0) path[depth] = best_e;
+                    if (sub == 0) { PathStep st; st.w = w_w; st.idx = best_e; st.n = w_n; ps[depth] = st; }
                     ++depth;
                     apply_known_legal(me, you, w_act);                                  // mcts.py:122
-                    if (cnt == 0 || depth >= t.path_cap) descending = false;            // child not expanded: this is the leaf
+                    if (cnt == 0 || depth >= path_cap) descending = false;              // child not expanded: this is the leaf
                     else first = w_first;
                 }
             }
         }
+        __syncwarp();                                                                   // the path is visible to every lane of its slot
 
         // ---------------- leaf: terminal backup, table hit (expand now), or a request for the network ----------------
         if (__any_sync(kFull, do_sim)) {
@@ -140,24 +167,23 @@ __global__ void __launch_bounds__(kAsBlock) k_as_advance(SelfPlayDev d, TreeDev 
                 lg = legal_moves(me, you);
                 terminal = depth > 0 && lg == 0 && legal_moves(you, me) == 0;           // mcts.py:127 (a root is never terminal here)
             }
-            __syncwarp();                                                               // path[] of this descent is visible to lane 0
             if (do_sim && terminal) {
-                if (sub == 0) {
-                    backup(E, path, depth, (double)winner(me, you));                    // mcts.py:129-130: terminal leaves are re-scored, never expanded
-                    t.sims_done[gs] = sd + 1;
-                }
+                backup_from_smem(E, ps, depth, (double)winner(me, you), sub);           // mcts.py:129-130: re-scored, never expanded
+                ++sd; dirty = true;
             } else if (do_sim) {
                 uint32_t h = 0;
                 bool hit = false;
                 if (p.eval_mode == kEvalCached) {
                     h = cache_index(t, me, you);
                     const ulonglong2 key = t.c_key[h];
-                    hit = key.x == me && key.y == you && t.c_gen[h] == p.gen;
+                    const uint32_t gen = t.c_gen[h];
+                    hit = key.x == me && key.y == you && gen == p.gen;
                 }
                 if (hit) {
                     const float* prow = t.c_priors + (size_t)h * 68;                    // masked, renormalised priors as the network wrote them
+                    const double value = (double)t.c_value[h];                          // value.item(), mcts.py:144
                     const int cnt = lg ? popc64(lg) : 1;                                // [64] = forced pass (bitboard.pyx:176-178)
-                    const int first = t.n_edges[gs];
+                    const int first = n_edges;
                     if (first + cnt > t.edge_cap) {
                         if (sub == 0) atomicExch(t.error_flag, 1);
                         run = false;
@@ -169,22 +195,20 @@ __global__ void __launch_bounds__(kAsBlock) k_as_advance(SelfPlayDev d, TreeDev 
                             ed.p = prow[action]; ed.action = (uint8_t)action;
                             E[first + k] = ed;
                         }
-                        if (sub == 0) {
-                            t.n_nodes[gs] += 1;
-                            t.n_edges[gs] = first + cnt;
-                            t.n_evals[gs] += 1;                                         // what the reference would have evaluated
-                            if (depth == 0) {
-                                t.root_count[gs] = cnt;
-                            } else {
-                                Edge* leaf = E + path[depth - 1];
+                        ++n_nodes; n_edges = first + cnt; ++n_evals; ++hits; dirty = true;  // n_evals: what the reference would have evaluated
+                        if (depth == 0) {
+                            rc = cnt;
+                        } else {
+                            if (sub == 0) {
+                                Edge* leaf = E + ps[depth - 1].idx;
                                 leaf->child_first = first; leaf->child_count = (uint8_t)cnt;
-                                backup(E, path, depth, (double)t.c_value[h]);           // value.item(), mcts.py:144
-                                t.sims_done[gs] = sd + 1;
                             }
-                            atomicAdd(&t.stats[1], 1ULL);
+                            backup_from_smem(E, ps, depth, value, sub);
+                            ++sd;
                         }
                     }
                 } else {
+                    for (int dd = sub; dd < depth; dd += kLanes) t.path[gs * t.path_cap + dd] = ps[dd].idx;   // k_tree_expand backs up from here
                     if (sub == 0) {
                         t.leaf_self[gs] = me; t.leaf_opp[gs] = you; t.leaf_legal[gs] = lg;
                         t.path_len[gs] = depth;
@@ -208,8 +232,6 @@ __global__ void __launch_bounds__(kAsBlock) k_as_advance(SelfPlayDev d, TreeDev 
         // ---------------- move (parallel_self_play.py:354-405), as k_sp_move ----------------
         if (__any_sync(kFull, do_move)) {
             const int cnt = do_move ? rc : 0;
-            int ply = 0, game = 0;
-            if (do_move) { ply = d.move_count[gs]; game = d.game_id[gs]; }
             int total = 0, best_n = -1, best_k = 0x7FFFFFFF;
             for (int k = sub; k < cnt; k += kLanes) {
                 const int nv = E[k].n;
@@ -233,7 +255,7 @@ __global__ void __launch_bounds__(kAsBlock) k_as_advance(SelfPlayDev d, TreeDev 
                 smp->self_b = me; smp->opp_b = you; smp->legal = legal_moves(me, you);
                 smp->game = game; smp->ply = (int16_t)ply; smp->value = 0; smp->n_children = (uint8_t)cnt;
                 smp->pad[0] = smp->pad[1] = smp->pad[2] = 0;
-                atomicAdd(&d.counters[4], (unsigned long long)t.n_evals[gs]);
+                atomicAdd(&d.counters[4], (unsigned long long)n_evals);
                 atomicAdd(&d.counters[6], 1ULL);
                 if (ply >= kMaxPlies) atomicExch(&d.counters[5], 1ULL);
                 // ---- choose the move (:379-382)
@@ -289,24 +311,32 @@ __global__ void __launch_bounds__(kAsBlock) k_as_advance(SelfPlayDev d, TreeDev 
                 }
             }
             __syncwarp();
-            if (over) {
-                if (sub == 0) {
-                    __threadfence();
-                    atomicAdd(&d.counters[1], 1ULL);
-                    d.self_b[gs] = kStartSelf; d.opp_b[gs] = kStartOpp; d.move_count[gs] = 0;
-                    d.game_id[gs] = next_game;
-                    d.active[gs] = next_game >= 0 ? 1 : 0;
+            if (do_move) {
+                ply = plies;
+                if (over) {
+                    if (sub == 0) {
+                        __threadfence();
+                        atomicAdd(&d.counters[1], 1ULL);
+                        d.self_b[gs] = kStartSelf; d.opp_b[gs] = kStartOpp; d.move_count[gs] = 0;
+                        d.game_id[gs] = next_game;
+                        d.active[gs] = next_game >= 0 ? 1 : 0;
+                    }
+                    me = kStartSelf; you = kStartOpp;                                   // board_class(); board.reset() (:338-341)
+                    ply = 0; game = next_game;
+                    if (next_game < 0) run = false;                                     // the campaign has no episode left for this slot
                 }
-                me = kStartSelf; you = kStartOpp;                                       // board_class(); board.reset() (:338-341)
-                if (next_game < 0) run = false;                                         // the campaign has no episode left for this slot
-            }
-            if (do_move && sub == 0) {                                                  // a fresh tree for the next search (mcts.py:71)
-                t.root_self[gs] = me; t.root_opp[gs] = you;
-                t.n_nodes[gs] = 0; t.n_edges[gs] = 0; t.n_evals[gs] = 0; t.sims_done[gs] = 0; t.path_len[gs] = 0;
-                t.root_count[gs] = 0; t.eval_slot[gs] = -1;
+                // a fresh tree for the next search (mcts.py:71)
+                root_me = me; root_you = you;
+                rc = 0; sd = 0; n_edges = 0; n_nodes = 0; n_evals = 0; dirty = true;
+                if (sub == 0) { t.root_self[gs] = me; t.root_opp[gs] = you; t.path_len[gs] = 0; t.eval_slot[gs] = -1; }
             }
         }
         __syncwarp();
+    }
+    // write the slot state back
+    if (dirty && sub == 0) {
+        t.root_count[gs] = rc; t.sims_done[gs] = sd; t.n_edges[gs] = n_edges; t.n_nodes[gs] = n_nodes; t.n_evals[gs] = n_evals;
+        if (hits) atomicAdd(&t.stats[1], (unsigned long long)hits);
     }
 }
 

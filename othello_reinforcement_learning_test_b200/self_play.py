@@ -163,7 +163,11 @@ class ParallelSelfPlayWorker:
         self.last_stats: dict = {}
 
     def _slots_for(self, num_episodes: int) -> int:
-        want = self.concurrent_games or max(self.num_parallel_games, min(num_episodes, self.DEFAULT_CONCURRENT_GAMES))
+        # an explicit `concurrent_games` is the engine's size, whatever a campaign asks for (a shorter campaign leaves
+        # slots idle; the trees, staging, cache and pinned buffer are allocated once)
+        if self.concurrent_games:
+            return max(1, int(self.concurrent_games))
+        want = max(self.num_parallel_games, min(num_episodes, self.DEFAULT_CONCURRENT_GAMES))
         return max(1, min(int(want), max(num_episodes, 1)))
 
     def _get_engine(self, num_episodes: int, add_noise: bool) -> SelfPlayEngine:
