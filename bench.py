@@ -327,6 +327,9 @@ def run_b200(args):
     engine = worker._get_engine(G, True)
     engine._pinned_out(G * 66)          # page-locked result buffer allocated once, outside the timed region (setup, like cudaMalloc)
     replay = pkg.ReplayBuffer(max_size=int(G * 64 * world), ctx=ctx) if world > 1 else None
+    gatherer = odist.DeviceSampleGather(dev) if world > 1 else None
+    if gatherer is not None:
+        gatherer.reserve(G * 64)        # receive buffer allocated once, outside the timed region
     ev = lambda: torch.cuda.Event(enable_timing=True)
     e0, e1, b0, b1, g0, g1 = ev(), ev(), ev(), ev(), ev(), ev()
     acc = {"e2e_ms": 0.0, "dev_ms": 0.0, "bcast_ms": 0.0, "gather_ms": 0.0, "samples": 0, "evals": 0, "h2d": 0, "d2h": 0,
@@ -345,9 +348,12 @@ def run_b200(args):
         if world > 1:                                                    # trajectories of every rank into the replay buffer,
             g0.record(stream)                                            # NCCL all-gather device to device
             dptr, cnt = worker._engine.samples_device()
-            gathered, total_cnt = odist.all_gather_samples_device(dptr, cnt, dev, episodes=episodes)
+            segments = gatherer.gather(dptr, cnt, G * 128, episodes=episodes)     # straight from the engine's buffer
             replay.clear()
-            replay.add_device(gathered, total_cnt)
+            total_cnt = 0
+            for seg, c in segments:
+                replay.add_device(seg, c)
+                total_cnt += c
             g1.record(stream)
         e1.record(stream)
         e1.synchronize()
@@ -535,11 +541,52 @@ def run_legs(args, pkg, ctx, t_start):
             out[name] = run_leg(pkg, ctx, name, **kw)
         except Exception as e:          # a leg must never take the headline down with it
             out[name] = {"error": str(e)[:200]}
+    try:
+        out["single_board_path"] = leg_single_board(pkg, ctx)
+    except Exception as e:
+        out["single_board_path"] = {"error": str(e)[:200]}
     if time.time() - t_start <= args.leg_deadline:
         try:
             out["reference_signature_e2e_4096_games"] = leg_reference_signature(args, pkg, ctx)
         except Exception as e:
             out["reference_signature_e2e_4096_games"] = {"error": str(e)[:200]}
+    return out
+
+
+def leg_single_board(pkg, ctx, games=20):
+    """The reference's per-move board calls (arena.py:106-119: is_terminal, get_legal_moves, make_move, then get_winner /
+    get_stone_counts at the end) on OthelloBitboard: one oth_board_step launch per move, everything else from its result.
+    Next to it the compiled reference board (Cython, oracle/_ref) doing the same loop on this host."""
+    def loop(Board):
+        n = 0
+        t0 = time.perf_counter()
+        for g in range(games):
+            b = Board()
+            while not b.is_terminal():
+                lm = b.get_legal_moves()
+                b.make_move(lm[(n + g) % len(lm)])
+                n += 1
+            b.get_winner(); b.get_stone_counts()
+        return 1e6 * (time.perf_counter() - t0) / n, n
+    loop(pkg.OthelloBitboard)
+    l0 = ctx.launch_count
+    us, moves = loop(pkg.OthelloBitboard)
+    out = {"us_per_move": us, "moves": moves, "launches_per_move": (ctx.launch_count - l0) / moves,
+           "what": "is_terminal + get_legal_moves + make_move per move through the reference-shaped class; one one-warp launch, result in a "
+                   "mapped page-locked mailbox (no allocation, no memcpy)"}
+    b = pkg.OthelloBitboard()
+    t0 = time.perf_counter()
+    for i in range(2000):
+        b.self_board = b.self_board            # drops the cached answers: every query is a launch
+        b.get_legal_moves_bits()
+    out["us_per_uncached_query"] = 1e6 * (time.perf_counter() - t0) / 2000
+    try:
+        from oracle import refload
+        Ref = refload.ref_bitboard_class()
+        if Ref is not None:
+            out["reference_cython_us_per_move"] = loop(Ref)[0]
+    except Exception as e:
+        out["reference_cython_error"] = str(e)[:120]
     return out
 
 

@@ -31,13 +31,16 @@ def pack_training_data(data) -> np.ndarray:
     if n == 0:
         return out
     w = (1 << np.arange(64, dtype=np.uint64))
-    states = np.stack([d[0] for d in data]).reshape(n, 3, 64)
+    states = np.asarray([d[0] for d in data], dtype=np.float32).reshape(n, 3, 64)
     for k, name in enumerate(("self_b", "opp_b", "legal")):
         out[name] = ((states[:, k] > 0.5).astype(np.uint64) * w).sum(axis=1, dtype=np.uint64)
-    pol = np.stack([np.asarray(d[1], np.float64) for d in data])                 # [n,65]
+    pol = np.asarray([d[1] for d in data], dtype=np.float64)                      # [n,65]
     counts = np.rint(pol * 65535.0)                                                # fallback: 1/65535 quantisation
     todo = np.ones(n, bool)
-    for total in range(1, 1025):                                                   # smallest N with p*N integral
+    # any N with p*N integral reproduces the distribution exactly (counts / sum is the same correctly rounded quotient);
+    # the usual simulation counts are tried first so that a campaign's samples resolve in one pass
+    common = [50, 100, 25, 200, 400, 800, 10, 20, 30, 40, 60, 64, 128, 256, 512, 1000, 1600]
+    for total in common + [t for t in range(1, 1025) if t not in common]:
         if not todo.any():
             break
         c = pol[todo] * total

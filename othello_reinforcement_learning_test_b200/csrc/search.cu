@@ -546,8 +546,10 @@ int SearchHost::evaluate(NetHost* net)
     }
     OTH_REQUIRE(net && net->loaded, OTH_ERR_STATE, "search: no network (or weights not loaded) and OTH_FLAG_EVAL_HASHNET not set");
     OTH_REQUIRE(net->ctx == ctx, OTH_ERR_ARG, "search: network belongs to a different context");
-    net->evals += (uint64_t)n;
-    return net_forward_device(net, t.batch_self, t.batch_opp, n, t.eval_policy, t.eval_value, kOutPriors, t.batch_count);
+    net->evals += (uint64_t)n_act;
+    // upper bound of the compacted batch = games that search this move (the device count in t.batch_count can only be
+    // smaller); a small bound sends the launch to the latency shape of the network without a read-back
+    return net_forward_device(net, t.batch_self, t.batch_opp, n_act, t.eval_policy, t.eval_value, kOutPriors, t.batch_count);
 }
 
 int SearchHost::run(NetHost* net, int sims, bool add_noise, uint64_t seed)

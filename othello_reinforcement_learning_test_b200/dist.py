@@ -87,34 +87,63 @@ _GAME_WORD = SAMPLE_DTYPE.fields["game"][1] // 4          # int32 index of the `
 _REC_WORDS = SAMPLE_DTYPE.itemsize // 4
 
 
+class DeviceSampleGather:
+    """All-gather of packed samples that already live in device memory, without a host hop and without staging copies.
+
+    NCCL's all-gather wants equally sized contributions: every rank contributes the first `biggest` records of its engine's
+    sample buffer (the buffer is at least that long; what lies behind a rank's own count is ignored), straight from the
+    engine's memory, into a receive buffer that is kept from call to call (grow-only).  Returns one (uint8 CUDA tensor,
+    count) segment per rank, in rank order, with globally unique episode ids when `episodes` is given; feed them to
+    `ReplayBuffer.add_device`."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.recv = None
+
+    def reserve(self, records_per_rank: int) -> None:
+        """Size the receive buffer up front (setup time, like cudaMalloc) for `records_per_rank` records from every rank."""
+        need = dist.get_world_size() * int(records_per_rank) * SAMPLE_DTYPE.itemsize
+        if self.recv is None or self.recv.numel() < need:
+            self.recv = None
+            self.recv = torch.empty(need + 4096, dtype=torch.uint8, device=self.device)
+
+    def gather(self, dev_ptr: int, count: int, capacity: int, episodes: int | None = None):
+        """`capacity`: records the memory at dev_ptr is known to hold (>= count)."""
+        world = dist.get_world_size()
+        rec = SAMPLE_DTYPE.itemsize
+        cnt = torch.tensor([count, -1 if episodes is None else episodes], dtype=torch.int64, device=self.device)
+        counts = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(counts, cnt)
+        episodes_per_rank = [int(c[1].item()) for c in counts]
+        counts = [int(c[0].item()) for c in counts]
+        biggest = max(max(counts), 1)
+        need = world * biggest * rec
+        if self.recv is None or self.recv.numel() < need:
+            self.recv = None                                  # release before growing
+            self.recv = torch.empty(int(need * 1.05) + 4096, dtype=torch.uint8, device=self.device)
+        out = self.recv[:need]
+        if biggest <= capacity:
+            mine = torch.as_tensor(_DevView(dev_ptr, biggest * rec), device=self.device)  # zero-copy view of the engine's buffer
+        else:                                                 # this rank's buffer is shorter than the largest contribution: pad a copy
+            mine = torch.zeros(biggest * rec, dtype=torch.uint8, device=self.device)
+            if count:
+                mine[: count * rec] = torch.as_tensor(_DevView(dev_ptr, count * rec), device=self.device)
+        dist.all_gather_into_tensor(out, mine)
+        if all(e >= 0 for e in episodes_per_rank):
+            words = out.view(torch.int32).view(world, biggest, _REC_WORDS)
+            base = 0
+            for r in range(1, world):
+                base += episodes_per_rank[r - 1]
+                if counts[r]:
+                    words[r, : counts[r], _GAME_WORD] += base
+        return [(out[r * biggest * rec: r * biggest * rec + c * rec], c) for r, c in enumerate(counts)]
+
+
 def all_gather_samples_device(dev_ptr: int, count: int, device: torch.device, episodes: int | None = None):
-    """All-gather packed samples that already live in device memory (oth_selfplay_samples_device) without a host
-    hop: returns (uint8 CUDA tensor holding every rank's records back to back in rank order, total count).
-    Feed it to a device ReplayBuffer with `ReplayBuffer.add_device`.  `episodes` = how many episodes this rank
-    played: when given, the `game` fields are offset on the device so that episode ids are globally unique."""
-    world = dist.get_world_size()
-    rec = SAMPLE_DTYPE.itemsize
-    cnt = torch.tensor([count, -1 if episodes is None else episodes], dtype=torch.int64, device=device)
-    counts = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(counts, cnt)
-    episodes_per_rank = [int(c[1].item()) for c in counts]
-    counts = [int(c[0].item()) for c in counts]
-    biggest = max(max(counts), 1)
-    mine = torch.zeros(biggest * rec, dtype=torch.uint8, device=device)
-    if count:
-        mine[: count * rec] = torch.as_tensor(_DevView(dev_ptr, count * rec), device=device)
-    gathered = torch.empty(world * biggest * rec, dtype=torch.uint8, device=device)
-    dist.all_gather_into_tensor(gathered, mine)
-    if all(e >= 0 for e in episodes_per_rank):
-        words = gathered.view(torch.int32).view(world, biggest, _REC_WORDS)
-        base = 0
-        for r in range(1, world):
-            base += episodes_per_rank[r - 1]
-            words[r, : counts[r], _GAME_WORD] += base
-    if all(c == biggest for c in counts):
-        return gathered, sum(counts)
-    packed = torch.cat([gathered[r * biggest * rec: r * biggest * rec + c * rec] for r, c in enumerate(counts)])
-    return packed, sum(counts)
+    """One-shot form of DeviceSampleGather: (uint8 CUDA tensor holding every rank's records back to back in rank order,
+    total count).  Prefer a kept DeviceSampleGather in a loop (no re-allocation, no concatenation)."""
+    segs = DeviceSampleGather(device).gather(dev_ptr, count, max(count, 1), episodes)
+    return torch.cat([t for t, _ in segs]), sum(c for _, c in segs)
 
 
 def renumber_games(samples_per_rank: list[np.ndarray]) -> np.ndarray:

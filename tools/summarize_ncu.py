@@ -58,10 +58,11 @@ if os.path.exists(lc):
     with open(os.path.join(out, f"{tag}_launches.txt"), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: per-kernel device time over the captured launch window\n")
         f.write("# (cold-cache, serialised: compare SHARES with bench.py's roofline.kernel_share_of_step, not absolutes)\n")
-        f.write("# command: bench.py --steps 1 --warmup 0 --no-cpu-baseline --games 37888, launches 1500..2100 of the campaign (plies ~10-14);\n")
-        f.write("# the network's share grows with the campaign size (more searches per launch): 89 % here, 97 % at the bench default\n")
+        f.write("# command: bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-legs --games 37888, launches 1500..2100 of the campaign;\n")
+        f.write("# the network's share grows with the campaign size (more searches per launch): ~82 % here, 97 % at the bench default\n")
         f.write("# of 303,104 games (roofline.kernel_share_of_step) -- ncu costs ~45 ms per intercepted launch, so the default size is\n")
-        f.write("# out of reach for a launch list.\n")
+        f.write("# out of reach for a launch list.  k_net_lat rows = launches that returned at once because the device-side batch\n")
+        f.write("# was above the latency shape's range (since then only issued when the ply's searching-game count allows it).\n")
         for k, v in sorted(tot.items(), key=lambda x: -x[1]):
             f.write(f"{k:60s} launches={cnt[k]:5d} total_ms={v / 1e6:10.3f} avg_us={v / cnt[k] / 1e3:10.1f} share={100 * v / s:5.1f}%\n")
 bj = os.path.join(src, "bench.json")
