@@ -331,8 +331,8 @@ def run_b200(args):
     if gatherer is not None:
         gatherer.reserve(G * 64)        # receive buffer allocated once, outside the timed region
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    e0, e1, b0, b1, g0, g1 = ev(), ev(), ev(), ev(), ev(), ev()
-    acc = {"e2e_ms": 0.0, "dev_ms": 0.0, "bcast_ms": 0.0, "gather_ms": 0.0, "samples": 0, "evals": 0, "h2d": 0, "d2h": 0,
+    e0, e1, b0, b1, g0, g1, s0 = ev(), ev(), ev(), ev(), ev(), ev(), ev()
+    acc = {"e2e_ms": 0.0, "dev_ms": 0.0, "bcast_ms": 0.0, "gather_ms": 0.0, "skew_ms": 0.0, "samples": 0, "evals": 0, "h2d": 0, "d2h": 0,
            "pos": 0, "hits": 0, "dups": 0, "coll": 0, "searches": 0, "ticks": 0, "gather_bytes": 0}
 
     def step(episodes, timed):
@@ -346,7 +346,9 @@ def run_b200(args):
         net.sync_from(model, force=True)                                 # fold BN + bf16 pack + H2D
         smp = worker.execute_episodes_packed(episodes, add_dirichlet_noise=True, reuse_buffer=True)   # campaign + D2H into pinned host memory
         if world > 1:                                                    # trajectories of every rank into the replay buffer,
-            g0.record(stream)                                            # NCCL all-gather device to device
+            s0.record(stream)                                            # NCCL all-gather device to device.  Ranks play different
+            dist.barrier()                                               # games and finish at different times: that wait is timed
+            g0.record(stream)                                            # apart from the collective itself
             dptr, cnt = worker._engine.samples_device()
             segments = gatherer.gather(dptr, cnt, G * 128, episodes=episodes)     # straight from the engine's buffer
             replay.clear()
@@ -367,7 +369,7 @@ def run_b200(args):
         acc["h2d"] += weight_upload_bytes(args.blocks, args.filters)
         acc["d2h"] += int(smp.size) * 168 + 64 * 130
         if world > 1:
-            acc["bcast_ms"] += b0.elapsed_time(b1); acc["gather_ms"] += g0.elapsed_time(g1)
+            acc["bcast_ms"] += b0.elapsed_time(b1); acc["gather_ms"] += g0.elapsed_time(g1); acc["skew_ms"] += s0.elapsed_time(g0)
             acc["gather_bytes"] += int(total_cnt) * 168
 
     for _ in range(args.warmup):
@@ -388,7 +390,7 @@ def run_b200(args):
     launches = ctx.launch_count - launches0
     timing = ctx.timing_read()
     ctx.timing_enable(False)
-    ms = torch.tensor([acc["dev_ms"], acc["e2e_ms"], acc["bcast_ms"], acc["gather_ms"]], dtype=torch.float64, device=dev)
+    ms = torch.tensor([acc["dev_ms"], acc["e2e_ms"], acc["bcast_ms"], acc["gather_ms"], acc["skew_ms"]], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(acc["samples"]), float(acc["evals"]), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -458,9 +460,12 @@ def run_b200(args):
     if world > 1:
         line["collectives"] = {"broadcast_ms_per_step": float(ms[2].item()) / args.steps, "all_gather_ms_per_step": float(ms[3].item()) / args.steps,
                                "all_gather_bytes_per_rank_per_step": acc["gather_bytes"] // args.steps,
+                               "rank_skew_wait_ms_per_step": float(ms[4].item()) / args.steps,
                                "share_of_e2e_step": (float(ms[2].item()) + float(ms[3].item())) / max_e2e_ms,
                                "what": "max over ranks; broadcast = one flat fp32 buffer of every parameter and buffer (NCCL), all-gather = "
-                                       "168-byte records device to device (NCCL) + copy into the device replay ring"}
+                                       "168-byte records device to device (NCCL, straight from the engine's buffer) + copy into the device "
+                                       "replay ring; rank_skew_wait = the barrier before the all-gather (ranks play different games and "
+                                       "finish at different times; the longest wait is the fastest rank's)"}
     secondary = {"tree_kernels": {"bound": "hbm (latency in practice)", "algorithmic_bytes": tree_bytes, "ms": tree_ms,
                                   "simulations_run": sims_run,
                                   "achieved": tree_bytes / (tree_ms / 1e3) / 1e9 if tree_ms else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -145,3 +145,19 @@ def test_campaigns_on_one_worker_draw_from_different_streams():
     assert first.tobytes() != second.tobytes()
     again = order(pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", **kw).execute_episodes_packed(32))
     assert again.tobytes() == first.tobytes()                          # same seed, same first campaign
+
+
+def test_async_schedule_honours_the_variant_flags():
+    """q_canonical / winner_black are read inside the run-until-miss kernel too: same records as lock-step."""
+    import othello_reinforcement_learning_test_b200 as pkg
+    kw = dict(num_simulations=30, temperature_threshold=10, num_parallel_games=16, c_puct=1.25, seed=3, concurrent_games=24, verbose=False,
+              q_canonical=True, winner_black=True)
+    order = lambda a: a[np.lexsort((a["ply"], a["game"]))]
+    a = order(pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", schedule="lockstep", **kw).execute_episodes_packed(60))
+    b = order(pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", schedule="async", **kw).execute_episodes_packed(60))
+    assert a.size == b.size and a.tobytes() == b.tobytes()
+    # root_n_sum with noise: per-game noise enters the search, the engine must fall back to lock-step by itself
+    w = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", schedule="async", root_n_sum=True, num_simulations=10,
+                                   num_parallel_games=4, concurrent_games=8, seed=1, verbose=False)
+    w.execute_episodes_packed(8, add_dirichlet_noise=True)
+    assert w.last_stats["schedule"] == "lockstep"

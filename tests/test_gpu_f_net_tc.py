@@ -171,3 +171,24 @@ def test_pair_engine_is_bit_identical_to_the_single_cta_engine(ctx, golden_games
             assert np.array_equal(a, b) and np.array_equal(av, bv), (n, out)
     b2, bv2 = two.forward(S, O, out="priors")
     assert np.array_equal(b, b2) and np.array_equal(bv, bv2)
+
+
+@pytest.mark.parametrize("nb,nf", [(5, 64), (10, 128)])
+def test_latency_shape_is_bit_identical_to_the_throughput_kernel(ctx, golden_games, nb, nf):
+    """k_net_lat (one tile per CTA, tensor-map TMA, batches of at most 256 positions) and k_net_tc compute the same sums in the
+    same order: identical bits for every output kind, on both sides of the 256-position boundary, for ragged batches, and
+    when the batch size is only known on the device (the search's compacted leaf batch launches both kernels)."""
+    from othello_reinforcement_learning_test_b200.net import InferenceNet
+    sd = net_oracle.make_state_dict(nb, nf, 11)
+    net = InferenceNet(nb, nf, ctx, engine="tcgen05"); net.load_state_dict(sd)
+    live = np.flatnonzero(golden_games["terminal"] == 0)
+    idx = np.random.default_rng(21).choice(live, 1000, replace=False)
+    S, O = golden_games["self_b"][idx], golden_games["opp_b"][idx]
+    for out in ("logprobs", "probs", "priors"):
+        big_p, big_v = net.forward(S, O, out=out)                          # 1,000 positions: the throughput kernel
+        for n in (1, 2, 3, 99, 255, 256):                                   # the latency shape
+            p, v = net.forward(S[:n], O[:n], out=out)
+            assert np.array_equal(p, big_p[:n]) and np.array_equal(v, big_v[:n]), (out, n)
+        for n in (257, 300, 593):                                           # just above the boundary: the throughput kernel again
+            p, v = net.forward(S[:n], O[:n], out=out)
+            assert np.array_equal(p, big_p[:n]) and np.array_equal(v, big_v[:n]), (out, n)

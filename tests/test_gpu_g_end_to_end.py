@@ -135,6 +135,23 @@ def test_async_schedule_equals_lockstep_with_the_network(ctx, nb, nf, games, slo
     assert got.tobytes() == want.tobytes() and auto.last_stats["schedule"] == "async"
 
 
+def test_searches_of_every_batch_size_agree_whatever_kernel_shape_evaluates_the_leaves(ctx, golden_games):
+    """oth_search_run hands the network a batch whose size is only known on the device.  With 300 boards the bound is above
+    the latency shape's 256 positions, so both network kernels are launched per step and the device count picks one; with
+    40 boards only the latency shape runs.  The visit counts of a board must not depend on which batch it was searched in."""
+    import othello_reinforcement_learning_test_b200 as pkg
+    from othello_reinforcement_learning_test_b200.net import OthelloResNet
+    torch.manual_seed(5)
+    model = OthelloResNet(5, 64).eval()
+    S, O = _positions(golden_games, 300, 23)
+    m = pkg.MCTS(model, "cuda", c_puct=1.0, eval_cache=True)
+    v300, q300, e300 = m.search_arrays(S, O, 40)
+    v40, q40, e40 = pkg.MCTS(model, "cuda", c_puct=1.0).search_arrays(S[:40], O[:40], 40)
+    assert np.array_equal(v300[:40], v40) and np.array_equal(q300[:40], q40) and np.array_equal(e300[:40], e40)
+    v1, q1, e1 = pkg.MCTS(model, "cuda", c_puct=1.0).search_arrays(S[7:8], O[7:8], 40)
+    assert np.array_equal(v300[7:8], v1) and np.array_equal(q300[7:8], q1)
+
+
 def test_packed_campaign_into_the_reusable_pinned_buffer(ctx):
     """execute_episodes_packed(reuse_buffer=True) is the same records, delivered as a view into one page-locked buffer."""
     import othello_reinforcement_learning_test_b200 as pkg
