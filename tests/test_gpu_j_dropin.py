@@ -23,7 +23,10 @@ def reference_callers():
     """sys.path / sys.modules set up the way a reference checkout with the drop-in installed looks; undone afterwards."""
     from oracle import refload
     import othello_reinforcement_learning_test_b200.dropin as dropin
-    root = refload.reference_root(bytecode=True)
+    try:
+        root = refload.reference_root(bytecode=True)
+    except RuntimeError as e:                       # oracle/_ref did not travel: nothing to drive the drop-in with
+        pytest.skip(str(e))
     refload.purge_reference_modules(keep_bitboard=False)
     sys.path.insert(0, root)
 
