@@ -7,10 +7,11 @@
 //
 //     root request -> simulations -> move (record, sample / arg-max, play, label + flush at game end, refill) -> next root ...
 //
-// and one launch of k_as_advance drives each slot through as many of those steps as the cache can answer; a slot only
-// stops when its leaf MISSES.  One tick = advance -> assign (elect one evaluator per distinct position) -> network on the
-// compacted misses -> expand (consume + insert).  Ticks per game = misses of that game (~0.3 x expansions) instead of
-// (1 + sims) x plies.  Every search is still the reference's serial search (one simulation of a game in flight, K = 1),
+// and one launch of k_as_advance drives each slot through as many of those steps as the cache can answer (up to a small
+// cap, see async_steps_per_tick); a slot stops when its leaf MISSES.  One tick = advance -> assign (elect one evaluator per
+// distinct position) -> network on the compacted misses -> expand (consume + insert).  Network launches per campaign =
+// misses of the slowest slot (~0.3-0.5 x its expansions) instead of (1 + sims) x plies: 2,365 instead of 3,332 for 100
+// games of 10x128 / 50 simulations.  Every search is still the reference's serial search (one simulation of a game in flight, K = 1),
 // so the records equal the lock-step schedule's byte for byte: select/expand/backup restate node.py:62-136 and
 // mcts.py:100-172 exactly as search.cu does, the move step restates parallel_self_play.py:354-405 as k_sp_move does.
 //
