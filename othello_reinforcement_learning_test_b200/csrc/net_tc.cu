@@ -174,8 +174,8 @@ __device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t in_off,
 // Tried and removed (B200, 10x128, 18,944 positions): thread-block clusters whose CTAs each fetch 1/CL of every ring stage
 // and multicast it to the cluster (cp.async.bulk ... multicast::cluster).  CL = 2: +2.4 % (+7.5 % with 16 KB copies), CL = 4:
 // half speed (cluster placement); a lone tile was not faster (the ~30 B/clk an SM's shared memory takes from bulk copies is
-// on the receiving side), and the outputs were not bit-identical to the unclustered kernel, which the evaluation cache
-// relies on.
+// on the receiving side), and the rank-1 CTA of every cluster returned wrong, run-to-run different outputs (a position-level
+// diff showed exactly the odd items off): its ring barriers let it run ahead of the data, so even the gain was not real.
 template <int F, int TILES>
 __global__ void __launch_bounds__(kThreads, 1)
 k_net_tc(const NetDev net, const uint64_t* __restrict__ self_b, const uint64_t* __restrict__ opp_b, int64_t n,
