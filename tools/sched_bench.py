@@ -17,6 +17,7 @@ ap.add_argument("--threshold", type=int, default=15)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--no-cache", action="store_true")
 ap.add_argument("--tag", default="")
+ap.add_argument("--no-timing", action="store_true", help="no per-kernel CUDA events (their records sit between the launches)")
 a = ap.parse_args()
 ctx = pkg.Context.default(0)
 torch.manual_seed(42)
@@ -27,7 +28,7 @@ w = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, model, torch.device("cuda"),
 net = w.batch_mcts._native_net()
 eng = w._get_engine(a.games, True)
 eng.play(net.handle, a.games)
-ctx.timing_enable(True)
+ctx.timing_enable(not a.no_timing)
 ms = ticks = launches = pos = evals = 0
 for _ in range(a.reps):
     eng.play(net.handle, a.games)
@@ -37,6 +38,6 @@ t = ctx.timing_read()
 print(json.dumps({"tag": a.tag, "games": a.games, "schedule": eng.last_stats["schedule"], "net": f"{a.blocks}x{a.filters}", "sims": a.sims,
                   "games_per_s": round(a.games * a.reps / (ms / 1e3), 1), "ms_per_campaign": round(ms / a.reps, 1),
                   "network_launches": ticks // a.reps, "us_per_network_launch_step": round(1e3 * ms / ticks, 1),
-                  "net_us_per_launch": round(1e3 * t["net"][0] / max(t["net"][1], 1), 1), "net_share": round(t["net"][0] / ms, 3),
-                  "tree_share": round(t["tree"][0] / ms, 3), "positions_per_expansion": round(pos / evals, 3),
+                  "net_us_per_launch": round(1e3 * t["net"][0] / max(t["net"][1], 1), 1) if not a.no_timing else None,
+                  "net_share": round(t["net"][0] / ms, 3), "tree_share": round(t["tree"][0] / ms, 3), "kernel_events": not a.no_timing, "positions_per_expansion": round(pos / evals, 3),
                   "env": {k: v for k, v in os.environ.items() if k.startswith("OTH_")}}))
