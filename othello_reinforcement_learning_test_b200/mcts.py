@@ -6,7 +6,7 @@ attributes, `search(board, num_simulations, temperature, add_dirichlet_noise) ->
 (np.float32[65], float)`, `get_action_probs`, `get_best_action`, `get_action_evaluations`,
 `search_batch`, `batch_predict`.
 
-Select / expand / backup run in csrc/search.cu (one warp per game).  The leaf evaluator is
+Select / expand / backup run in csrc/search.cu (a group of 8 lanes per game, four games per warp).  The leaf evaluator is
   * the native tcgen05 network when `model` is an OthelloResNet-shaped torch module
     (weights are re-read whenever the module's tensors change), or
   * any other callable `model(x[B,3,8,8]) -> (log_probs, value)` through the

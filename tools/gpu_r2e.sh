@@ -1,5 +1,7 @@
 #!/bin/bash
 # Weight-stream experiments on k_net_tc: 16 KB stage groups (g2), cluster multicast (CL = 2, 4), one tile per CTA.
+# (Kept as the record of how profiles/r02_weight_stream_experiments_1.txt was produced; the OTH_TC_CLUSTER* knobs belonged to the
+#  cluster-multicast experiment, which was removed from net_tc.cu afterwards -- see DESIGN.md section 4.)
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out/r2e
