@@ -154,3 +154,40 @@ def test_bf16_emulation_error_budget(golden_net):
     lp, v = net_oracle.forward_bf16_emulated(m.state_dict(), x)
     assert np.abs(np.exp(lp.numpy()) - np.exp(g["init42_5x64_logp"])).max() < 2e-2
     assert np.abs(v.numpy().reshape(-1) - g["init42_5x64_value"]).max() < 2e-2
+
+
+def test_network_oracle_against_the_bulk_reference_outputs(golden_net_bulk):
+    """oracle/net_oracle.forward_fp32 (the fp32 restatement the GPU tests are judged against) reproduces what the
+    reference's own OthelloResNet returned for the seed-42 initialisation (tests/golden/net_bulk_ref.npz, first 96 of the
+    10,240 positions; torch CPU kernels may differ in the last bits between machines, hence 1e-5)."""
+    from othello_reinforcement_learning_test_b200.net import OthelloResNet      # same construction order as the reference module
+    g = golden_net_bulk
+    torch.manual_seed(42)
+    sd = OthelloResNet(10, 128).state_dict()
+    x = net_oracle.boards_to_tensor(g["self_b"][:96], g["opp_b"][:96])
+    lp, v = net_oracle.forward_fp32(sd, x)
+    assert np.abs(np.exp(lp.numpy()) - np.exp(g["init42_10x128_logp"][:96])).max() < 1e-5
+    assert np.abs(v.numpy().reshape(-1) - g["init42_10x128_value"][:96]).max() < 1e-5
+    # the fixture is what it says: distinct, non-terminal self-play positions
+    S, O = g["self_b"], g["opp_b"]
+    assert S.size == 10240 and len(set(zip(S.tolist(), O.tolist()))) == S.size and (S & O == 0).all()
+    t, _ = cref.terminal_winner_batch(S, O)
+    assert not t.any()
+
+
+def test_symmetry_restatement_against_the_compiled_reference(golden_symmetry):
+    """The host-side restatement of get_symmetries (np.rot90 k times, then np.flip of the columns; bitboard.pyx:338-370) as
+    used by augment_data_with_symmetries(full=True), against the images the COMPILED reference board returned."""
+    from othello_reinforcement_learning_test_b200.self_play import augment_data_with_symmetries
+    g = golden_symmetry
+    S, O = g["self_b"], g["opp_b"]
+    states = cref.tensor_input_batch(S, O)
+    data = [(states[i], g["pi"][i], float(i % 3 - 1)) for i in range(S.size)]
+    full = augment_data_with_symmetries(data, None, full=True)
+    assert len(full) == 8 * S.size
+    w8 = (1 << np.arange(64, dtype=np.uint64))
+    for i in range(S.size):
+        for k in range(8):
+            st, p, v = full[8 * i + k]
+            bits = ((st.reshape(3, 64) > 0.5).astype(np.uint64) * w8).sum(axis=1, dtype=np.uint64)
+            assert np.array_equal(bits, g["planes"][i, k]) and np.array_equal(p, g["policy"][i, k]) and v == data[i][2]
