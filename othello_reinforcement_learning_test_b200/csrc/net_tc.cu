@@ -40,11 +40,12 @@ namespace tc {
 constexpr int kStages = OTH_TC_STAGES;          // weight ring depth (8 KB slots); must divide 6 (stem) and 18 (one issue trip)
 constexpr int kCopySplit = OTH_TC_COPY_SPLIT;   // bulk copies per ring stage (experiment knob: requests in flight per byte)
 #ifndef OTH_TC_STAGE_GROUP
-#define OTH_TC_STAGE_GROUP 1
+#define OTH_TC_STAGE_GROUP 2
 #endif
 // Consecutive ring stages fetched by ONE bulk copy.  A bulk copy costs ~52 cycles + bytes / 35.4 B/clk on one SM (measured:
 // 2 KB copies 110 cycles, 8 KB copies 283), and with 8 KB per copy the weight stream (283 cycles per stage), not the tensor
 // core (256 cycles per stage for two tiles), sets the layer time.  Weights lie in streaming order, so a group is contiguous.
+// Two stages (16 KB) per copy: +1.7 % on the kernel alone, +1.0 % on the full self-play step (A/B on one box, alternating).
 constexpr int kGroup = OTH_TC_STAGE_GROUP;
 constexpr int kGroups = kStages / kGroup;       // barrier pairs: one bar_full / bar_empty per group
 static_assert(kStages % kGroup == 0 && 18 % kGroup == 0 && (kGroup == 1 || kGroup == 2), "stage groups: 1 or 2 stages per copy");
