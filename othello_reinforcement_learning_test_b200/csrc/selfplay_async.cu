@@ -365,7 +365,8 @@ int SelfPlayHost::run_async(NetHost* net, int64_t num_episodes)
     if (!use_cache) view.cache_mask = 0;
 
     const int grid = (int)((d.slots + kSlotsPerBlock - 1) / kSlotsPerBlock);
-    const int check_every = 8;                            // termination is polled, not awaited: the launch queue stays full
+    const int check_every = 16;                           // termination is polled, not awaited: the launch queue stays full
+                                                          // (a poll drains it once; ticks after the last game ends are empty launches)
     // every tick resolves at least one simulation of every unfinished slot
     const int64_t rounds = (num_episodes + d.slots - 1) / d.slots + 1;
     const int64_t max_ticks = rounds * kMaxPlies * (int64_t)(cfg.num_simulations + 3) + 64;
@@ -389,7 +390,7 @@ int SelfPlayHost::run_async(NetHost* net, int64_t num_episodes)
             OTH_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
             OTH_REQUIRE(h_counters[5] == 0, OTH_ERR_CAPACITY, "oth_selfplay_run: trajectory buffer overflow");
             if ((int64_t)h_counters[1] >= num_episodes) break;
-            if ((tick + 1) % (16 * check_every) == 0 && (rc = s.check_overflow())) return rc;   // a full edge pool would stall its slot forever
+            if ((tick + 1) % (8 * check_every) == 0 && (rc = s.check_overflow())) return rc;   // a full edge pool would stall its slot forever
         }
     }
     moves_played += (uint64_t)h_counters[6];
