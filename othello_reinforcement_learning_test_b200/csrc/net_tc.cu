@@ -3,7 +3,7 @@
 // One persistent CTA per SM walks over "items" of 4 boards (2 tiles x 128 GEMM rows).  The
 // whole network runs inside the kernel: activations never leave shared memory, accumulators
 // live in TMEM, and only the BN-folded bf16 weights stream in (L2-resident, 1-D bulk-TMA
-// copies into a 6-slot ring, each slot consumed by both tiles).
+// copies of two 8 KB stages each into a 6-stage ring, each stage consumed by both tiles).
 //
 //   warps 0-3  : tile 0 epilogue (TMEM -> +bias/+skip/ReLU -> bf16 -> shared), input planes; the last layer's
 //                epilogue also applies the three 1x1 head convolutions to the row it holds in registers
