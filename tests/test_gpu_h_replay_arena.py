@@ -215,3 +215,40 @@ def test_single_board_step_is_one_call_and_matches_the_oracle(golden_games):
     assert ctx.launch_count - l0 == n_moves
     print(f"\\nsingle-board path: {1e6 * dt / n_moves:.1f} us per move incl. is_terminal/get_legal_moves/get_winner/get_stone_counts/"
           f"get_tensor_input ({n_moves} moves, 1 launch each)")
+
+
+def test_device_sample_gather_into_the_replay_ring_single_rank():
+    """The N > 1 data path of bench.py / INTEGRATION section 4 on one GPU (NCCL group of one rank): trajectories go from the
+    engine's device buffer through DeviceSampleGather straight into the device replay ring -- no host hop -- and come out
+    of the ring exactly as the host copy of the same campaign says."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    import othello_reinforcement_learning_test_b200 as pkg
+    from othello_reinforcement_learning_test_b200 import dist as odist
+    from othello_reinforcement_learning_test_b200.self_play import samples_to_arrays
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        w = pkg.ParallelSelfPlayWorker(pkg.OthelloBitboard, None, "cuda", num_simulations=12, temperature_threshold=15,
+                                       num_parallel_games=8, concurrent_games=48, seed=8, verbose=False)
+        host = w.execute_episodes_packed(48)
+        dptr, cnt = w._engine.samples_device()
+        assert cnt == host.size
+        gat = odist.DeviceSampleGather(torch.device("cuda", 0))
+        gat.reserve(48 * 70)
+        segs = gat.gather(dptr, cnt, 48 * 128, episodes=48)
+        assert len(segs) == 1 and segs[0][1] == cnt
+        buf = pkg.ReplayBuffer(max_size=cnt + 10)
+        for seg, c in segs:
+            buf.add_device(seg, c)
+        torch.cuda.synchronize()
+        assert len(buf) == cnt
+        st, po, va = buf.gather(np.arange(cnt))
+        want_st, want_po, want_va = samples_to_arrays(host, sort=False)          # ring order == the engine's flush order
+        assert np.array_equal(st, want_st) and np.array_equal(po, want_po) and np.array_equal(va[:, 0], want_va.astype(np.float32))
+        # a too-short source buffer is padded, not over-read
+        segs2 = gat.gather(dptr, cnt, cnt, episodes=48)
+        assert segs2[0][1] == cnt and bytes(segs2[0][0].cpu().numpy().tobytes()) == host.tobytes()
+    finally:
+        dist.destroy_process_group()
