@@ -503,6 +503,12 @@ def run_b200(args):
                                   "note": "BASELINE config 1, one game per thread in registers"}
         if not args.no_legs:
             line["legs"] = run_legs(args, pkg, ctx, t_start)
+            rs = line["legs"].get("reference_signature_e2e_4096_games", {})
+            if "reference_signature" in rs:       # the list-of-tuples route next to the packed one, where a reader looks for e2e
+                line["e2e"]["reference_signature_4096_games"] = {
+                    "list_api_games_per_s": rs["reference_signature"]["games_per_s"], "packed_api_games_per_s": rs["packed"]["games_per_s"],
+                    "what": "host wall clock of execute_episodes() -> ReplayBuffer.add(list) -> sample(256) vs execute_episodes_packed() -> "
+                            "add_from_worker -> sample_torch(256) on a 4,096-game campaign (legs.reference_signature_e2e_4096_games)"}
         if not args.no_cpu_baseline:
             try:
                 arm = reference_arm(args)
